@@ -1,0 +1,569 @@
+// fkb_api.cu -- the extern "C" boundary of include/findkmer_b200.h: context, device entry points and
+// the host-buffer (end-to-end) pipeline.  Replaces the call `headNode = findKmer(headNode, &baseCounter,
+// baseStatistics, &TotalNumSequencesN)` of the reference's main() (findKmer/src/findKmer.cpp:1320).
+#include <cuda_runtime.h>
+
+#include <errno.h>
+#include <fcntl.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "findkmer_b200.h"
+#include "fkb_kernels.cuh"
+#include "fkb_loader.h"
+
+struct fkb_context {
+    int device = 0;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    size_t hbm_bytes = 0;
+    std::string err;
+    uint64_t launches = 0;
+    int forced_variant = 0;
+
+    cudaStream_t s_pipe = nullptr;  // host pipeline: copies and kernels, in order
+    cudaStream_t s_aux = nullptr;   // zeroing that may overlap the first copies
+
+    // finalize scratch
+    unsigned long long *d_scratch = nullptr;
+    fkb_counts *d_counts = nullptr;
+    fkb_counts *h_counts = nullptr;  // pinned
+
+    // host pipeline buffers (grown on demand, kept for reuse)
+    uint8_t *d_stream = nullptr;
+    size_t d_stream_cap = 0;
+    uint32_t *d_table = nullptr;
+    uint8_t *d_flags = nullptr;
+    fkb_partials *d_partials = nullptr;
+    int table_k = 0;
+
+    // pinned staging ring for the loader
+    static constexpr int kSlots = 12;
+    size_t slot_bytes = 0;
+    uint8_t *slots[kSlots] = {nullptr};
+    cudaEvent_t slot_free[kSlots] = {nullptr};
+};
+
+namespace {
+
+constexpr size_t kBlockBytes = 4u << 20;  // loader block: 4 MiB of raw file per strip task
+
+int fail(fkb_context *ctx, int status, const char *fmt, ...)
+{
+    if (ctx) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        ctx->err = buf;
+    }
+    return status;
+}
+
+#define FKB_CUDA(ctx, expr)                                                                             \
+    do {                                                                                                \
+        cudaError_t e__ = (expr);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail((ctx), FKB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+fkb::LaunchInfo launch_info(const fkb_context *ctx) { return fkb::LaunchInfo{ctx->sm_count, ctx->forced_variant}; }
+
+int check_k(fkb_context *ctx, int k)
+{
+    if (k < 1 || k > FKB_MAX_K) return fail(ctx, FKB_ERR_BAD_K, "%d is not a valid value for k (dense engine supports 1..%d)", k, FKB_MAX_K);
+    return FKB_OK;
+}
+
+int ensure_table(fkb_context *ctx, int k)
+{
+    if (ctx->table_k == k && ctx->d_table) return FKB_OK;
+    if (ctx->d_table) cudaFree(ctx->d_table);
+    if (ctx->d_flags) cudaFree(ctx->d_flags);
+    ctx->d_table = nullptr;
+    ctx->d_flags = nullptr;
+    ctx->table_k = 0;
+    FKB_CUDA(ctx, cudaMalloc(&ctx->d_table, fkb_table_entries(k) * sizeof(uint32_t)));
+    FKB_CUDA(ctx, cudaMalloc(&ctx->d_flags, fkb_prefix_flags_bytes(k)));
+    if (!ctx->d_partials) FKB_CUDA(ctx, cudaMalloc(&ctx->d_partials, sizeof(fkb_partials)));
+    ctx->table_k = k;
+    return FKB_OK;
+}
+
+int ensure_stream(fkb_context *ctx, size_t bytes)
+{
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes <= ctx->d_stream_cap) return FKB_OK;
+    if (ctx->d_stream) cudaFree(ctx->d_stream);
+    ctx->d_stream = nullptr;
+    ctx->d_stream_cap = 0;
+    FKB_CUDA(ctx, cudaMalloc(&ctx->d_stream, bytes));
+    ctx->d_stream_cap = bytes;
+    return FKB_OK;
+}
+
+int ensure_slots(fkb_context *ctx)
+{
+    if (ctx->slots[0]) return FKB_OK;
+    ctx->slot_bytes = kBlockBytes + 64;
+    for (int i = 0; i < fkb_context::kSlots; ++i) {
+        FKB_CUDA(ctx, cudaHostAlloc((void **)&ctx->slots[i], ctx->slot_bytes, cudaHostAllocDefault));
+        FKB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->slot_free[i], cudaEventDisableTiming));
+    }
+    return FKB_OK;
+}
+
+int status_from_counts(fkb_context *ctx, const fkb_counts &c)
+{
+    if (c.rollover)
+        return fail(ctx, FKB_ERR_COUNTER_ROLLOVER,
+                    "COUNTER ROLLOVER DETECTED: a 32-bit k-mer/prefix counter would have wrapped (reference findKmer.cpp:640-648)");
+    return FKB_OK;
+}
+
+// finalize + copy back table and counts, then drain the pipeline stream
+int finish_host(fkb_context *ctx, int k, uint64_t stream_bytes, uint32_t *table, fkb_counts *counts)
+{
+    int launches = 0;
+    FKB_CUDA(ctx, fkb::launch_finalize(launch_info(ctx), k, ctx->d_table, ctx->d_flags, ctx->d_partials, stream_bytes, ctx->d_counts,
+                                       ctx->d_scratch, ctx->s_pipe, &launches));
+    ctx->launches += launches;
+    FKB_CUDA(ctx, cudaMemcpyAsync(table, ctx->d_table, fkb_table_entries(k) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->s_pipe));
+    FKB_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, sizeof(fkb_counts), cudaMemcpyDeviceToHost, ctx->s_pipe));
+    FKB_CUDA(ctx, cudaStreamSynchronize(ctx->s_pipe));
+    *counts = *ctx->h_counts;
+    return status_from_counts(ctx, *counts);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *fkb_version(void) { return "findkmer_b200 0.1 (sm_100a)"; }
+
+const char *fkb_status_string(int status)
+{
+    switch (status) {
+    case FKB_OK: return "ok";
+    case FKB_ERR_EMPTY_INPUT: return "Sequence File Is Empty";
+    case FKB_ERR_UNTERMINATED_HEADER: return "'>' header line without a terminating newline (the reference never returns on this input)";
+    case FKB_ERR_COUNTER_ROLLOVER: return "COUNTER ROLLOVER DETECTED";
+    case FKB_ERR_BAD_K: return "not a valid value for k";
+    case FKB_ERR_NOMEM: return "host memory allocation failed";
+    case FKB_ERR_CUDA: return "CUDA failure";
+    case FKB_ERR_BAD_ARG: return "bad argument";
+    case FKB_ERR_IO: return "I/O failure";
+    case FKB_ERR_ZERO_BASE_PROBABILITY: return "Division overflow detected in statistics.";
+    default: return "unknown status";
+    }
+}
+
+size_t fkb_table_entries(int k) { return (k >= 1 && k <= FKB_MAX_K) ? ((size_t)1 << (2 * k)) : 0; }
+
+size_t fkb_prefix_flags_bytes(int k)
+{
+    if (k < 1 || k > FKB_MAX_K) return 0;
+    size_t n = (((size_t)1 << (2 * k)) - 4) / 3;  // sum_{d=1..k-1} 4^d
+    return n < 16 ? 16 : n;
+}
+
+int fkb_create(int device, fkb_context **out)
+{
+    if (!out) return FKB_ERR_BAD_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) return FKB_ERR_CUDA;  // no CPU fallback exists
+    fkb_context *ctx = new (std::nothrow) fkb_context();
+    if (!ctx) return FKB_ERR_NOMEM;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete ctx;
+        return FKB_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->cc_major = prop.major;
+    ctx->cc_minor = prop.minor;
+    ctx->hbm_bytes = prop.totalGlobalMem;
+    if (prop.major != 10) {  // the kernels are built for sm_100a only
+        delete ctx;
+        return FKB_ERR_CUDA;
+    }
+    const char *v = getenv("FKB_VARIANT");
+    ctx->forced_variant = v ? atoi(v) : 0;
+    bool ok = cudaStreamCreateWithFlags(&ctx->s_pipe, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaMalloc(&ctx->d_scratch, sizeof(unsigned long long) * fkb::kFinalizeScratchWords) == cudaSuccess &&
+              cudaMalloc(&ctx->d_counts, sizeof(fkb_counts)) == cudaSuccess &&
+              cudaHostAlloc((void **)&ctx->h_counts, sizeof(fkb_counts), cudaHostAllocDefault) == cudaSuccess;
+    if (!ok) {
+        fkb_destroy(ctx);
+        return FKB_ERR_CUDA;
+    }
+    *out = ctx;
+    return FKB_OK;
+}
+
+void fkb_destroy(fkb_context *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < fkb_context::kSlots; ++i) {
+        if (ctx->slots[i]) cudaFreeHost(ctx->slots[i]);
+        if (ctx->slot_free[i]) cudaEventDestroy(ctx->slot_free[i]);
+    }
+    if (ctx->d_stream) cudaFree(ctx->d_stream);
+    if (ctx->d_table) cudaFree(ctx->d_table);
+    if (ctx->d_flags) cudaFree(ctx->d_flags);
+    if (ctx->d_partials) cudaFree(ctx->d_partials);
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    if (ctx->d_counts) cudaFree(ctx->d_counts);
+    if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+    if (ctx->s_pipe) cudaStreamDestroy(ctx->s_pipe);
+    if (ctx->s_aux) cudaStreamDestroy(ctx->s_aux);
+    delete ctx;
+}
+
+const char *fkb_last_error(const fkb_context *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+uint64_t fkb_launch_count(const fkb_context *ctx) { return ctx ? ctx->launches : 0; }
+
+int fkb_device_info(fkb_context *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *hbm_bytes)
+{
+    if (!ctx) return FKB_ERR_BAD_ARG;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (cc_major) *cc_major = ctx->cc_major;
+    if (cc_minor) *cc_minor = ctx->cc_minor;
+    if (hbm_bytes) *hbm_bytes = ctx->hbm_bytes;
+    return FKB_OK;
+}
+
+int fkb_alloc_pinned(fkb_context *ctx, size_t bytes, void **ptr)
+{
+    if (!ctx || !ptr) return FKB_ERR_BAD_ARG;
+    FKB_CUDA(ctx, cudaSetDevice(ctx->device));
+    FKB_CUDA(ctx, cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return FKB_OK;
+}
+
+int fkb_free_pinned(fkb_context *ctx, void *ptr)
+{
+    if (!ctx) return FKB_ERR_BAD_ARG;
+    FKB_CUDA(ctx, cudaFreeHost(ptr));
+    return FKB_OK;
+}
+
+// ---- host loader ---------------------------------------------------------------------------------
+int fkb_strip_fasta(const uint8_t *fasta, size_t len, uint8_t *stream, size_t *stream_len, int n_threads)
+{
+    if (!stream_len || (len && (!fasta || !stream))) return FKB_ERR_BAD_ARG;
+    *stream_len = 0;
+    if (len == 0) return FKB_ERR_EMPTY_INPUT;
+    if (n_threads <= 0) n_threads = fkb::default_host_threads();
+    const size_t n_blocks = (len + kBlockBytes - 1) / kBlockBytes;
+    if ((size_t)n_threads > n_blocks) n_threads = (int)n_blocks;
+
+    struct Block { fkb::StripResult r; bool hdr; size_t off; };
+    std::vector<Block> blocks(n_blocks);
+    auto run_pass = [&](auto &&fn) {
+        std::atomic<size_t> next{0};
+        std::vector<std::thread> pool;
+        auto worker = [&] {
+            for (;;) {
+                size_t i = next.fetch_add(1);
+                if (i >= n_blocks) break;
+                fn(i);
+            }
+        };
+        for (int t = 1; t < n_threads; ++t) pool.emplace_back(worker);
+        worker();
+        for (auto &th : pool) th.join();
+    };
+    // pass A: sizes
+    run_pass([&](size_t i) {
+        size_t a = i * kBlockBytes, b = a + kBlockBytes < len ? a + kBlockBytes : len;
+        blocks[i].hdr = fkb::in_header_at(fasta, a);
+        blocks[i].r = fkb::strip_block_count(fasta, a, b, blocks[i].hdr);
+    });
+    size_t total = 0, last = n_blocks;  // `last`: block that holds the terminating 0xFF, if any
+    for (size_t i = 0; i < n_blocks; ++i) {
+        blocks[i].off = total;
+        total += blocks[i].r.n_out;
+        if (blocks[i].r.stop_pos != SIZE_MAX) { last = i; break; }
+    }
+    const size_t used = last == n_blocks ? n_blocks : last + 1;
+    // pass B: write (private scratch per task keeps the vector stores' slack out of the neighbours' output)
+    std::atomic<bool> nomem{false};
+    run_pass([&](size_t i) {
+        if (i >= used) return;
+        size_t a = i * kBlockBytes, b = a + kBlockBytes < len ? a + kBlockBytes : len;
+        thread_local std::vector<uint8_t> scratch;
+        try { scratch.resize(kBlockBytes + 64); } catch (...) { nomem = true; return; }
+        fkb::StripResult r = fkb::strip_block(fasta, a, b, blocks[i].hdr, scratch.data());
+        memcpy(stream + blocks[i].off, scratch.data(), r.n_out);
+    });
+    if (nomem) return FKB_ERR_NOMEM;
+    *stream_len = total;
+    if (last == n_blocks && blocks[n_blocks - 1].r.ends_in_header) return FKB_ERR_UNTERMINATED_HEADER;
+    return FKB_OK;
+}
+
+// ---- device entry points -------------------------------------------------------------------------
+int fkb_zero_device(fkb_context *ctx, int k, uint32_t *d_table, uint8_t *d_flags, fkb_partials *d_partials, void *cuda_stream)
+{
+    if (!ctx) return FKB_ERR_BAD_ARG;
+    if (int s = check_k(ctx, k)) return s;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (d_table) FKB_CUDA(ctx, cudaMemsetAsync(d_table, 0, fkb_table_entries(k) * sizeof(uint32_t), st));
+    if (d_flags) FKB_CUDA(ctx, cudaMemsetAsync(d_flags, 0, fkb_prefix_flags_bytes(k), st));
+    if (d_partials) FKB_CUDA(ctx, cudaMemsetAsync(d_partials, 0, sizeof(fkb_partials), st));
+    return FKB_OK;
+}
+
+int fkb_count_stream_device(fkb_context *ctx, const uint8_t *d_stream, uint64_t begin, uint64_t end, int k, uint32_t *d_table,
+                            uint8_t *d_flags, fkb_partials *d_partials, void *cuda_stream)
+{
+    if (!ctx || !d_table || !d_flags || !d_partials) return FKB_ERR_BAD_ARG;
+    if (int s = check_k(ctx, k)) return s;
+    if (end < begin) return fail(ctx, FKB_ERR_BAD_ARG, "end < begin");
+    if (end == begin) return FKB_OK;
+    if (!d_stream || ((uintptr_t)d_stream & 15)) return fail(ctx, FKB_ERR_BAD_ARG, "d_stream must be a 16-byte aligned device pointer");
+    int launches = 0;
+    FKB_CUDA(ctx, fkb::launch_count(launch_info(ctx), d_stream, begin, end, k, d_table, d_flags, d_partials, (cudaStream_t)cuda_stream, &launches));
+    ctx->launches += launches;
+    return FKB_OK;
+}
+
+int fkb_finalize_device(fkb_context *ctx, int k, const uint32_t *d_table, uint8_t *d_flags, const fkb_partials *d_partials,
+                        uint64_t stream_bytes, fkb_counts *d_counts, void *cuda_stream)
+{
+    if (!ctx || !d_table || !d_flags || !d_partials || !d_counts) return FKB_ERR_BAD_ARG;
+    if (int s = check_k(ctx, k)) return s;
+    int launches = 0;
+    FKB_CUDA(ctx, fkb::launch_finalize(launch_info(ctx), k, d_table, d_flags, d_partials, stream_bytes, d_counts, ctx->d_scratch,
+                                       (cudaStream_t)cuda_stream, &launches));
+    ctx->launches += launches;
+    return FKB_OK;
+}
+
+// ---- host-buffer pipelines -----------------------------------------------------------------------
+int fkb_count_stream_host(fkb_context *ctx, const uint8_t *stream, size_t len, int k, uint32_t *table, fkb_counts *counts)
+{
+    if (!ctx || !table || !counts || (len && !stream)) return FKB_ERR_BAD_ARG;
+    if (int s = check_k(ctx, k)) return s;
+    FKB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (int s = ensure_table(ctx, k)) return s;
+    if (int s = ensure_stream(ctx, len + 64)) return s;
+    if (int s = fkb_zero_device(ctx, k, ctx->d_table, ctx->d_flags, ctx->d_partials, ctx->s_pipe)) return s;
+    // chunked so the count of chunk i overlaps the copy of chunk i+1 (copy engine vs SMs, one ordered stream
+    // is enough: a kernel on [a,b) only needs bytes < b, and the copies are issued in order on a second stream)
+    const size_t chunk = 64u << 20;
+    cudaEvent_t ev;
+    FKB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (size_t a = 0; a < len; a += chunk) {
+        size_t b = a + chunk < len ? a + chunk : len;
+        cudaError_t e = cudaMemcpyAsync(ctx->d_stream + a, stream + a, b - a, cudaMemcpyHostToDevice, ctx->s_aux);
+        if (e == cudaSuccess) e = cudaEventRecord(ev, ctx->s_aux);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->s_pipe, ev, 0);
+        if (e != cudaSuccess) { cudaEventDestroy(ev); FKB_CUDA(ctx, e); }
+        int launches = 0;
+        e = fkb::launch_count(launch_info(ctx), ctx->d_stream, a, b, k, ctx->d_table, ctx->d_flags, ctx->d_partials, ctx->s_pipe, &launches);
+        ctx->launches += launches;
+        if (e != cudaSuccess) { cudaEventDestroy(ev); FKB_CUDA(ctx, e); }
+    }
+    cudaEventDestroy(ev);
+    return finish_host(ctx, k, len, table, counts);
+}
+
+int fkb_count_fasta_host(fkb_context *ctx, const uint8_t *fasta, size_t len, int k, uint32_t *table, fkb_counts *counts)
+{
+    if (!ctx || !table || !counts || (len && !fasta)) return FKB_ERR_BAD_ARG;
+    if (int s = check_k(ctx, k)) return s;
+    if (len == 0) return fail(ctx, FKB_ERR_EMPTY_INPUT, "Sequence File Is Empty");
+    FKB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (int s = ensure_table(ctx, k)) return s;
+    if (int s = ensure_stream(ctx, len + 64)) return s;
+    if (int s = ensure_slots(ctx)) return s;
+    if (int s = fkb_zero_device(ctx, k, ctx->d_table, ctx->d_flags, ctx->d_partials, ctx->s_pipe)) return s;
+
+    // Loader pipeline: host threads strip 4 MiB blocks of the file into pinned slots; this thread commits the
+    // blocks IN ORDER -- H2D copy to the running offset in the device stream, then a count kernel over the
+    // newly arrived byte range (its left halo is already there) -- and recycles the slot when its copy is done.
+    const size_t n_blocks = (len + kBlockBytes - 1) / kBlockBytes;
+    const int n_slots = fkb_context::kSlots;
+    int n_threads = fkb::default_host_threads();
+    if ((size_t)n_threads > n_blocks) n_threads = (int)n_blocks;
+
+    struct Task { fkb::StripResult r; bool done = false; };
+    std::vector<Task> tasks(n_blocks);
+    std::mutex mu;
+    std::condition_variable cv_done, cv_slot;
+    std::atomic<size_t> next{0};
+    size_t released = 0;  // blocks whose H2D copy has completed, in order: their slots may be reused (guarded by mu)
+    bool abort_all = false;
+
+    auto worker = [&] {
+        for (;;) {
+            size_t i = next.fetch_add(1);
+            if (i >= n_blocks) return;
+            {   // slot i % n_slots last held block i - n_slots
+                std::unique_lock<std::mutex> lk(mu);
+                cv_slot.wait(lk, [&] { return abort_all || i < released + (size_t)n_slots; });
+                if (abort_all) return;
+            }
+            size_t a = i * kBlockBytes, b = a + kBlockBytes < len ? a + kBlockBytes : len;
+            fkb::StripResult r = fkb::strip_block(fasta, a, b, fkb::in_header_at(fasta, a), ctx->slots[i % n_slots]);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                tasks[i].r = r;
+                tasks[i].done = true;
+            }
+            cv_done.notify_all();
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; ++t) pool.emplace_back(worker);
+
+    size_t dev_off = 0, counted = 0;
+    bool stopped = false, ends_in_header = false;
+    cudaError_t cuda_err = cudaSuccess;
+    const size_t count_every = 32u << 20;  // one count kernel per >= 32 MiB of newly arrived stream
+    auto release_one = [&] {
+        std::lock_guard<std::mutex> lk(mu);
+        ++released;
+        cv_slot.notify_all();
+    };
+    for (size_t i = 0; i < n_blocks && cuda_err == cudaSuccess && !stopped; ++i) {
+        // wait for block i; while waiting, retire finished copies so the workers get their slots back
+        for (;;) {
+            size_t rel;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                if (tasks[i].done) break;
+                rel = released;
+                if (rel >= i) {  // nothing outstanding: the workers cannot be starved of slots
+                    cv_done.wait(lk, [&] { return tasks[i].done; });
+                    break;
+                }
+            }
+            cuda_err = cudaEventSynchronize(ctx->slot_free[rel % n_slots]);
+            if (cuda_err != cudaSuccess) break;
+            release_one();
+        }
+        if (cuda_err != cudaSuccess) break;
+        const fkb::StripResult r = tasks[i].r;
+        const int slot = (int)(i % n_slots);
+        if (r.n_out) {
+            cuda_err = cudaMemcpyAsync(ctx->d_stream + dev_off, ctx->slots[slot], r.n_out, cudaMemcpyHostToDevice, ctx->s_pipe);
+            dev_off += r.n_out;
+        }
+        if (cuda_err == cudaSuccess) cuda_err = cudaEventRecord(ctx->slot_free[slot], ctx->s_pipe);
+        ends_in_header = r.ends_in_header;
+        if (r.stop_pos != SIZE_MAX) {  // byte 0xFF outside a header: the reference's loop ends here
+            stopped = true;
+            ends_in_header = false;
+        }
+        const bool last = stopped || i + 1 == n_blocks;
+        if (cuda_err == cudaSuccess && dev_off > counted && (dev_off - counted >= count_every || last)) {
+            int launches = 0;
+            cuda_err = fkb::launch_count(launch_info(ctx), ctx->d_stream, counted, dev_off, k, ctx->d_table, ctx->d_flags, ctx->d_partials,
+                                         ctx->s_pipe, &launches);
+            ctx->launches += launches;
+            counted = dev_off;
+        }
+        while (cuda_err == cudaSuccess) {  // opportunistic retire
+            size_t rel;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                rel = released;
+            }
+            if (rel > i || cudaEventQuery(ctx->slot_free[rel % n_slots]) != cudaSuccess) break;
+            release_one();
+        }
+    }
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        abort_all = true;
+    }
+    cv_slot.notify_all();
+    for (auto &th : pool) th.join();
+    if (cuda_err != cudaSuccess) {
+        cudaStreamSynchronize(ctx->s_pipe);
+        return fail(ctx, FKB_ERR_CUDA, "loader pipeline: %s", cudaGetErrorString(cuda_err));
+    }
+    if (ends_in_header) {
+        cudaStreamSynchronize(ctx->s_pipe);
+        return fail(ctx, FKB_ERR_UNTERMINATED_HEADER, "%s", fkb_status_string(FKB_ERR_UNTERMINATED_HEADER));
+    }
+    return finish_host(ctx, k, dev_off, table, counts);
+}
+
+int fkb_count_file(fkb_context *ctx, const char *path, int k, uint32_t *table, fkb_counts *counts)
+{
+    if (!ctx || !path) return FKB_ERR_BAD_ARG;
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(ctx, FKB_ERR_IO, "Sequence file failed to open: %s: %s", path, strerror(errno));
+    struct stat st;
+    if (fstat(fd, &st) != 0) {
+        close(fd);
+        return fail(ctx, FKB_ERR_IO, "fstat(%s): %s", path, strerror(errno));
+    }
+    if (st.st_size == 0) {
+        close(fd);
+        return fail(ctx, FKB_ERR_EMPTY_INPUT, "Sequence File Is Empty");
+    }
+    void *map = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (map == MAP_FAILED) return fail(ctx, FKB_ERR_IO, "mmap(%s): %s", path, strerror(errno));
+    madvise(map, (size_t)st.st_size, MADV_SEQUENTIAL | MADV_WILLNEED);
+    int s = fkb_count_fasta_host(ctx, (const uint8_t *)map, (size_t)st.st_size, k, table, counts);
+    munmap(map, (size_t)st.st_size);
+    return s;
+}
+
+// ---- synthetic inputs ----------------------------------------------------------------------------
+int fkb_synth_fasta_device(fkb_context *ctx, uint8_t *d_out, uint64_t total_bytes, int n_records, const uint64_t *rec_offsets,
+                           const uint64_t *rec_base0, const uint8_t *headers, int header_len, int line_width, uint64_t seed,
+                           int n_runs, int soft_mask, void *cuda_stream)
+{
+    if (!ctx || !d_out || !rec_offsets || !rec_base0 || !headers || n_records < 1 || header_len < 2) return FKB_ERR_BAD_ARG;
+    if ((uintptr_t)d_out & 15) return fail(ctx, FKB_ERR_BAD_ARG, "d_out must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    uint64_t *d_off = nullptr, *d_b0 = nullptr;
+    uint8_t *d_hdr = nullptr;
+    size_t nb = sizeof(uint64_t) * (size_t)(n_records + 1), nh = (size_t)n_records * header_len;
+    FKB_CUDA(ctx, cudaMalloc(&d_off, nb));
+    FKB_CUDA(ctx, cudaMalloc(&d_b0, nb));
+    FKB_CUDA(ctx, cudaMalloc(&d_hdr, nh));
+    FKB_CUDA(ctx, cudaMemcpyAsync(d_off, rec_offsets, nb, cudaMemcpyHostToDevice, st));
+    FKB_CUDA(ctx, cudaMemcpyAsync(d_b0, rec_base0, nb, cudaMemcpyHostToDevice, st));
+    FKB_CUDA(ctx, cudaMemcpyAsync(d_hdr, headers, nh, cudaMemcpyHostToDevice, st));
+    int launches = 0;
+    cudaError_t e = fkb::launch_synth(launch_info(ctx), d_out, total_bytes, n_records, d_off, d_b0, d_hdr, header_len, line_width, seed,
+                                      n_runs, soft_mask, st, &launches);
+    ctx->launches += launches;
+    cudaError_t e2 = cudaStreamSynchronize(st);  // the temporaries are freed below
+    cudaFree(d_off);
+    cudaFree(d_b0);
+    cudaFree(d_hdr);
+    FKB_CUDA(ctx, e);
+    FKB_CUDA(ctx, e2);
+    return FKB_OK;
+}
+
+}  // extern "C"

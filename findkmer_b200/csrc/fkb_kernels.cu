@@ -1,0 +1,395 @@
+// fkb_kernels.cu -- hand-written sm_100a kernels of the k-mer counting path.
+//
+// Replaces (result-identically, not line by line) the reference's per-byte scan
+//   findKmer()                     findKmer/src/findKmer.cpp:962-1069
+//   base2int()                     :567-589
+//   shift_left_and_insert()        :947-958      -> a 2k-bit rolling register
+//   tree_create()/node_branch_enter_and_create()/node_create()  :612-690 -> dense uint32[4^k] table
+//
+// Input is the STRIPPED stream (include/findkmer_b200.h "stream contract"): no '\n', one '>' per
+// header.  Device rule: byte in {A,C,G,T} => code 0..3, anything else => window reset.
+//
+// Work decomposition: the stream is cut into 64-byte thread chunks; a thread reads its chunk plus the
+// 16 bytes in front of it (k <= 16, so 16 bytes of left context decide every window that ends in the
+// chunk AND whether a run's length is exactly k -- the reference's `seqSize == k` branch, :1044).
+// A window is counted by the thread (and the shard) that owns its LAST byte.
+#include "fkb_kernels.cuh"
+
+namespace fkb {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kChunk = 64;  // bytes owned per thread per iteration
+
+__host__ __device__ inline uint64_t flags_offset(int d) { return ((1ull << (2 * d)) - 4ull) / 3ull; }  // sum_{e<d} 4^e
+
+// 128-bit read-only load.  The stream is read once; neighbouring lanes share 32-byte sectors across the
+// five loads of an iteration, so L1 allocation is kept (no .no_allocate).
+__device__ __forceinline__ uint4 ldg128(const uint8_t *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// bytes [off, off+16) of the stream with everything outside [0, limit) read as 0 (a reset byte)
+__device__ __forceinline__ uint4 load16_guarded(const uint8_t *s, int64_t off, uint64_t limit)
+{
+    if (off >= 0 && (uint64_t)off + 16 <= limit) return ldg128(s + off);
+    uint32_t w[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 16; ++i) {
+        int64_t p = off + i;
+        if (p >= 0 && (uint64_t)p < limit) w[i >> 2] |= (uint32_t)s[p] << (8 * (i & 3));
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__device__ __forceinline__ void red_add_u32(uint32_t *addr, uint32_t v)
+{
+    asm volatile("red.global.add.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Per-thread scan state: the rolling register and the current run length (the reference's seqSize,
+// findKmer.cpp:977, saturating is unnecessary: a thread sees at most 16 + 64 bytes).
+struct Scan {
+    uint32_t kmer;
+    int run;
+};
+
+// ASCII -> 2-bit code for A,C,G,T (A0 C1 G2 T3, base2int :569-576) and validity.
+// code = bit1^bit2 : bit1 of (c>>1); letters: A 0x41, C 0x43, G 0x47, T 0x54.
+__device__ __forceinline__ uint32_t base_code(uint32_t c) { return ((c >> 1) ^ (c >> 2)) & 3u; }
+__device__ __forceinline__ bool base_valid(uint32_t c, uint32_t code) { return c == ((0x54474341u >> (code * 8)) & 0xffu); }
+
+// context-only step (left halo): no counting
+__device__ __forceinline__ void step_context(Scan &s, uint32_t c, uint32_t mask)
+{
+    uint32_t code = base_code(c);
+    s.kmer = ((s.kmer << 2) | code) & mask;
+    s.run = base_valid(c, code) ? s.run + 1 : 0;
+}
+
+struct Tally {
+    uint32_t windows;   // positions with run >= k
+    uint32_t unknown;   // bytes outside {A,C,G,T,N,'>'}
+    uint32_t valid;     // A,C,G,T bytes
+};
+
+// Rare events, off the fast path (once per run, and k-1 times per run):
+//  run == k : the reference adds all k bases of the first window to baseStatistics (:1050-1056); the LAST
+//             base is recovered from the table at finalize, the first k-1 go to head_base here.
+//  run <  k : the reference inserts the run so far as a short path (:1059-1062) => a depth-`run` trie node;
+//             recorded as a prefix flag, and as a visit of the depth-1 node of the run's first base.
+__device__ __noinline__ void rare_event(uint32_t kmer, int run, int k, uint8_t *flags, fkb_partials *P)
+{
+    if (run == k) {
+        uint32_t head = kmer >> 2;
+        uint32_t cnt[4] = {0, 0, 0, 0};
+        for (int i = 0; i < k - 1; ++i) {
+            cnt[head & 3u]++;
+            head >>= 2;
+        }
+        for (int b = 0; b < 4; ++b)
+            if (cnt[b]) atomicAdd(&P->head_base[b], (unsigned long long)cnt[b]);
+        atomicAdd(&P->runs_ge_k, 1ull);
+    } else {  // 1 <= run < k
+        uint32_t prefix = kmer & ((1u << (2 * run)) - 1u);
+        flags[flags_offset(run) + prefix] = 1;
+        atomicAdd(&P->short_first[prefix >> (2 * (run - 1))], 1ull);
+    }
+}
+
+template <bool EDGE>
+__device__ __forceinline__ void step_owned(Scan &s, uint32_t c, uint32_t mask, int k, uint32_t *table, uint8_t *flags,
+                                           fkb_partials *P, Tally &t, uint64_t pos, uint64_t begin, uint64_t end)
+{
+    uint32_t code = base_code(c);
+    bool valid = base_valid(c, code);
+    s.kmer = ((s.kmer << 2) | code) & mask;
+    s.run = valid ? s.run + 1 : 0;
+    bool own = EDGE ? (pos >= begin && pos < end) : true;
+    if (own) {
+        t.valid += valid;
+        t.unknown += (!valid && c != 'N' && c != '>');
+        if (s.run >= k) {
+            red_add_u32(table + s.kmer, 1u);
+            t.windows++;
+        }
+        if ((unsigned)(s.run - 1) < (unsigned)k) rare_event(s.kmer, s.run, k, flags, P);
+    }
+}
+
+template <bool EDGE>
+__device__ __forceinline__ void scan_word(Scan &s, uint32_t w, uint32_t mask, int k, uint32_t *table, uint8_t *flags,
+                                          fkb_partials *P, Tally &t, uint64_t pos, uint64_t begin, uint64_t end)
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j) step_owned<EDGE>(s, (w >> (8 * j)) & 0xffu, mask, k, table, flags, P, t, pos + j, begin, end);
+}
+
+// ------------------------------------------------------------------------------------------------
+// VARIANT_DIRECT: fused encode + count, one red.global.add.u32 per window.
+// The 4^k table (16 MiB at k = 11) is L2-resident; the atomics never reach HBM.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) count_direct_kernel(const uint8_t *__restrict__ s, uint64_t begin, uint64_t end, int k,
+                                                                uint32_t *__restrict__ table, uint8_t *__restrict__ flags,
+                                                                fkb_partials *__restrict__ P)
+{
+    const uint32_t mask = (k == 16) ? 0xffffffffu : ((1u << (2 * k)) - 1u);
+    const uint64_t base = begin & ~15ull;                      // chunks are 16-byte aligned in the stream
+    const uint64_t n_chunks = (end - base + kChunk - 1) / kChunk;
+    Tally t = {0, 0, 0};
+
+    for (uint64_t c = (uint64_t)blockIdx.x * kThreads + threadIdx.x; c < n_chunks; c += (uint64_t)gridDim.x * kThreads) {
+        const uint64_t p0 = base + c * kChunk;
+        const bool edge = (p0 < begin) || (p0 + kChunk > end) || (p0 < 16);
+        Scan sc = {0u, 0};
+        if (!edge) {
+            uint4 h = ldg128(s + p0 - 16);
+            uint4 v0 = ldg128(s + p0), v1 = ldg128(s + p0 + 16), v2 = ldg128(s + p0 + 32), v3 = ldg128(s + p0 + 48);
+            const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) step_context(sc, (hw[i] >> (8 * j)) & 0xffu, mask);
+            const uint32_t w[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
+#pragma unroll
+            for (int i = 0; i < 16; ++i) scan_word<false>(sc, w[i], mask, k, table, flags, P, t, p0 + 4 * i, begin, end);
+        } else {
+            uint4 h = load16_guarded(s, (int64_t)p0 - 16, end);
+            const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+            for (int i = 0; i < 4; ++i)
+                for (int j = 0; j < 4; ++j) step_context(sc, (hw[i] >> (8 * j)) & 0xffu, mask);
+            for (int g = 0; g < 4; ++g) {
+                uint4 v = load16_guarded(s, (int64_t)(p0 + 16 * g), end);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                for (int i = 0; i < 4; ++i) scan_word<true>(sc, w[i], mask, k, table, flags, P, t, p0 + 16 * g + 4 * i, begin, end);
+            }
+        }
+    }
+    unsigned long long win = warp_sum(t.windows), unk = warp_sum(t.unknown), val = warp_sum(t.valid);
+    if ((threadIdx.x & 31) == 0) {
+        if (win) atomicAdd(&P->n_windows, win);
+        if (unk) atomicAdd(&P->unknown_chars, unk);
+        if (val) atomicAdd(&P->valid_bases, val);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize: (table, prefix flags, partials) -> fkb_counts
+//   scratch[0]      sum of table               (must equal partials.n_windows, else a counter wrapped)
+//   scratch[1..4]   sum of table over k-mers whose LAST  base is b   (baseStatistics, :1041)
+//   scratch[5..8]   sum of table over k-mers whose FIRST base is b   (depth-1 trie node visits, :640)
+//   scratch[9]      number of trie nodes below the head
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) finalize_table_kernel(const uint32_t *__restrict__ table, int k, uint8_t *__restrict__ flags,
+                                                                  unsigned long long *__restrict__ scratch)
+{
+    const uint64_t groups = 1ull << (2 * (k - 1));  // groups of 4 sibling leaves
+    unsigned long long tot = 0, last[4] = {0, 0, 0, 0}, first[4] = {0, 0, 0, 0}, nodes = 0;
+    for (uint64_t g = (uint64_t)blockIdx.x * kThreads + threadIdx.x; g < groups; g += (uint64_t)gridDim.x * kThreads) {
+        uint4 v = reinterpret_cast<const uint4 *>(table)[g];
+        unsigned long long sum = (unsigned long long)v.x + v.y + v.z + v.w;
+        tot += sum;
+        last[0] += v.x; last[1] += v.y; last[2] += v.z; last[3] += v.w;
+        if (k == 1) {
+            first[0] += v.x; first[1] += v.y; first[2] += v.z; first[3] += v.w;
+        } else {
+            uint32_t fb = (uint32_t)(g >> (2 * (k - 2)));
+            first[0] += (fb == 0) ? sum : 0; first[1] += (fb == 1) ? sum : 0;
+            first[2] += (fb == 2) ? sum : 0; first[3] += (fb == 3) ? sum : 0;
+        }
+        nodes += (v.x != 0) + (v.y != 0) + (v.z != 0) + (v.w != 0);
+        if (k > 1 && sum != 0) flags[flags_offset(k - 1) + g] = 1;
+    }
+    tot = warp_sum(tot); nodes = warp_sum(nodes);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) { last[b] = warp_sum(last[b]); first[b] = warp_sum(first[b]); }
+    if ((threadIdx.x & 31) == 0) {
+        if (tot) atomicAdd(&scratch[0], tot);
+        for (int b = 0; b < 4; ++b) {
+            if (last[b]) atomicAdd(&scratch[1 + b], last[b]);
+            if (first[b]) atomicAdd(&scratch[5 + b], first[b]);
+        }
+        if (nodes) atomicAdd(&scratch[9], nodes);
+    }
+}
+
+// one trie depth d (1 <= d <= k-1): count present nodes, propagate presence to depth d-1
+__global__ void __launch_bounds__(kThreads) finalize_depth_kernel(uint8_t *__restrict__ flags, int d, unsigned long long *__restrict__ scratch)
+{
+    const uint64_t groups = 1ull << (2 * (d - 1));
+    const uint32_t *lvl = reinterpret_cast<const uint32_t *>(flags + flags_offset(d));
+    unsigned long long nodes = 0;
+    for (uint64_t g = (uint64_t)blockIdx.x * kThreads + threadIdx.x; g < groups; g += (uint64_t)gridDim.x * kThreads) {
+        uint32_t v = lvl[g];
+        nodes += ((v & 0xffu) != 0) + ((v & 0xff00u) != 0) + ((v & 0xff0000u) != 0) + ((v & 0xff000000u) != 0);
+        if (d > 1 && v != 0) flags[flags_offset(d - 1) + g] = 1;
+    }
+    nodes = warp_sum(nodes);
+    if ((threadIdx.x & 31) == 0 && nodes) atomicAdd(&scratch[9], nodes);
+}
+
+__global__ void finalize_counts_kernel(const unsigned long long *__restrict__ scratch, const fkb_partials *__restrict__ P,
+                                       uint64_t stream_bytes, fkb_counts *__restrict__ out)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    fkb_counts c;
+    c.n_kmers = scratch[0];
+    c.base_total = 0;
+    unsigned long long worst_visits = 0;
+    for (int b = 0; b < 4; ++b) {
+        c.base_count[b] = scratch[1 + b] + P->head_base[b];
+        c.base_total += c.base_count[b];
+        unsigned long long visits = scratch[5 + b] + P->short_first[b];
+        worst_visits = visits > worst_visits ? visits : worst_visits;
+    }
+    c.node_count = scratch[9] ? scratch[9] + 1 : 0;  // + the lazily created head node (:666-670)
+    c.unknown_chars = P->unknown_chars;
+    c.stream_bytes = stream_bytes;
+    c.runs_ge_k = P->runs_ge_k;
+    // rollover (:640-648): a trie node visited 2^32 times.  Depth-1 nodes are visited at least as often as any
+    // of their descendants, so they wrap first; a wrapped table shows up as sum(table) != independent window count.
+    c.rollover = (worst_visits >= (1ull << 32)) || (scratch[0] != P->n_windows);
+    c.valid_bases = P->valid_bases;
+    *out = c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// synthetic FASTA generator: bit-identical twin of findkmer_b200/synth.py::render()
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x)
+{
+    uint64_t z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__constant__ uint32_t c_run_quantiles[16] = {32, 98, 170, 247, 330, 421, 520, 629, 752, 891, 1052, 1242, 1474, 1773, 2197, 3466};
+
+__device__ __forceinline__ uint8_t synth_letter(uint64_t g, uint64_t seed, int n_runs, int soft_mask)
+{
+    uint8_t out = (uint8_t)((0x54474341u >> (8 * (uint32_t)(splitmix64(seed + g) >> 62))) & 0xffu);
+    if (soft_mask) {
+        uint64_t slot = g / 3000ull;
+        uint64_t h = splitmix64((seed ^ 0xC2B2AE3D27D4EB4Full) + slot);
+        uint64_t ln = ((uint64_t)c_run_quantiles[h & 15] * 3ull) / 10ull;
+        uint64_t start = (h >> 8) % (3000ull - ln);
+        if ((g % 3000ull) - start < ln) out |= 0x20;
+    }
+    if (n_runs) {
+        uint64_t slot = g / 20000ull;
+        uint64_t h = splitmix64((seed ^ 0x9E3779B97F4A7C15ull) + slot);
+        uint64_t ln = c_run_quantiles[h & 15];
+        uint64_t start = (h >> 8) % (20000ull - ln);
+        if ((g % 20000ull) - start < ln) out = 'N';
+    }
+    return out;
+}
+
+__global__ void __launch_bounds__(kThreads) synth_fasta_kernel(uint8_t *__restrict__ out, uint64_t total_bytes, int n_records,
+                                                               const uint64_t *__restrict__ rec_off, const uint64_t *__restrict__ rec_base0,
+                                                               const uint8_t *__restrict__ headers, int header_len, int line_width,
+                                                               uint64_t seed, int n_runs, int soft_mask)
+{
+    // each thread renders 16 consecutive bytes and stores them as one 128-bit word
+    const uint64_t n_groups = (total_bytes + 15) / 16;
+    for (uint64_t gi = (uint64_t)blockIdx.x * kThreads + threadIdx.x; gi < n_groups; gi += (uint64_t)gridDim.x * kThreads) {
+        uint32_t w[4] = {0, 0, 0, 0};
+        uint64_t p = gi * 16;
+        // record of the first byte by binary search; later bytes advance linearly
+        int lo = 0, hi = n_records;  // rec_off[lo] <= p < rec_off[hi]
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (rec_off[mid] <= p) lo = mid; else hi = mid;
+        }
+        int r = lo;
+        for (int i = 0; i < 16; ++i, ++p) {
+            if (p >= total_bytes) break;
+            while (r + 1 < n_records && p >= rec_off[r + 1]) ++r;
+            uint64_t o = p - rec_off[r];
+            uint8_t ch;
+            if (o < (uint64_t)header_len) {
+                ch = headers[(uint64_t)r * header_len + o];
+            } else {
+                o -= header_len;
+                uint64_t nb = rec_base0[r + 1] - rec_base0[r];
+                if (line_width == 0) {
+                    ch = (o == nb) ? (uint8_t)'\n' : synth_letter(rec_base0[r] + o, seed, n_runs, soft_mask);
+                } else {
+                    uint64_t q = o / (uint64_t)(line_width + 1), col = o % (uint64_t)(line_width + 1);
+                    uint64_t bi = q * line_width + col;
+                    ch = (col == (uint64_t)line_width || bi >= nb) ? (uint8_t)'\n' : synth_letter(rec_base0[r] + bi, seed, n_runs, soft_mask);
+                }
+            }
+            w[i >> 2] |= (uint32_t)ch << (8 * (i & 3));
+        }
+        if (gi * 16 + 16 <= total_bytes) {
+            reinterpret_cast<uint4 *>(out)[gi] = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {
+            for (uint64_t i = 0; gi * 16 + i < total_bytes; ++i) out[gi * 16 + i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
+        }
+    }
+}
+
+inline int grid_for(uint64_t items_per_thread_units, int sm_count, int ctas_per_sm)
+{
+    uint64_t need = (items_per_thread_units + kThreads - 1) / kThreads;
+    uint64_t cap = (uint64_t)sm_count * ctas_per_sm;  // a whole number of waves: multiple of the SM count
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+}  // namespace
+
+cudaError_t launch_count(const LaunchInfo &li, const uint8_t *d_stream, uint64_t begin, uint64_t end, int k, uint32_t *d_table,
+                         uint8_t *d_flags, fkb_partials *d_partials, cudaStream_t st, int *launches)
+{
+    if (end <= begin) return cudaSuccess;
+    const uint64_t base = begin & ~15ull;
+    const uint64_t n_chunks = (end - base + kChunk - 1) / kChunk;
+    int grid = grid_for(n_chunks, li.sm_count, 8);
+    count_direct_kernel<<<grid, kThreads, 0, st>>>(d_stream, begin, end, k, d_table, d_flags, d_partials);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_finalize(const LaunchInfo &li, int k, const uint32_t *d_table, uint8_t *d_flags, const fkb_partials *d_partials,
+                            uint64_t stream_bytes, fkb_counts *d_counts, unsigned long long *d_scratch, cudaStream_t st, int *launches)
+{
+    cudaError_t e = cudaMemsetAsync(d_scratch, 0, sizeof(unsigned long long) * kFinalizeScratchWords, st);
+    if (e != cudaSuccess) return e;
+    finalize_table_kernel<<<grid_for(1ull << (2 * (k - 1)), li.sm_count, 8), kThreads, 0, st>>>(d_table, k, d_flags, d_scratch);
+    if (launches) ++*launches;
+    for (int d = k - 1; d >= 1; --d) {
+        finalize_depth_kernel<<<grid_for(1ull << (2 * (d - 1)), li.sm_count, 8), kThreads, 0, st>>>(d_flags, d, d_scratch);
+        if (launches) ++*launches;
+    }
+    finalize_counts_kernel<<<1, 32, 0, st>>>(d_scratch, d_partials, stream_bytes, d_counts);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_synth(const LaunchInfo &li, uint8_t *d_out, uint64_t total_bytes, int n_records, const uint64_t *d_rec_offsets,
+                         const uint64_t *d_rec_base0, const uint8_t *d_headers, int header_len, int line_width, uint64_t seed,
+                         int n_runs, int soft_mask, cudaStream_t st, int *launches)
+{
+    if (total_bytes == 0) return cudaSuccess;
+    synth_fasta_kernel<<<grid_for((total_bytes + 15) / 16, li.sm_count, 8), kThreads, 0, st>>>(
+        d_out, total_bytes, n_records, d_rec_offsets, d_rec_base0, d_headers, header_len, line_width, seed, n_runs, soft_mask);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+}  // namespace fkb

@@ -1,0 +1,156 @@
+// fkb_loader.cpp -- host sequence loader: record and line stripping (the "stream contract").
+//
+// Restates, as a block-parallel filter, what the reference's scan loop does with three bytes
+// (findKmer/src/findKmer.cpp:988-1011):
+//   '\n'  -> dropped (windows span line breaks, :1011)
+//   '>'   -> ONE '>' byte is emitted (it resets the window, :994) and everything through the next '\n'
+//            is dropped (:999/:1005)
+//   0xFF  -> outside a header it ends the scan (fgetc() stored in a `char` aliases EOF, :975,:988)
+// Every other byte is copied verbatim; the device decides what is a base.
+#include "fkb_loader.h"
+
+#include <string.h>
+#include <thread>
+
+#include <immintrin.h>
+
+namespace fkb {
+
+int default_host_threads()
+{
+    const char *env = getenv("FKB_HOST_THREADS");
+    if (env && atoi(env) > 0) return atoi(env);
+    unsigned hc = std::thread::hardware_concurrency();
+    if (hc == 0) hc = 4;
+    return (int)(hc > 32 ? 32 : hc);
+}
+
+bool in_header_at(const uint8_t *buf, size_t pos)
+{
+    if (pos == 0) return false;
+    const uint8_t *nl = (const uint8_t *)memrchr(buf, '\n', pos);
+    size_t line_start = nl ? (size_t)(nl - buf) + 1 : 0;
+    return memchr(buf + line_start, '>', pos - line_start) != nullptr;
+}
+
+namespace {
+
+// portable scan: index of the first byte in [p,b) that is '\n', '>' or 0xFF
+inline size_t next_special_scalar(const uint8_t *buf, size_t p, size_t b)
+{
+    while (p < b) {
+        uint8_t c = buf[p];
+        if (c == '\n' || c == '>' || c == 0xFF) break;
+        ++p;
+    }
+    return p;
+}
+
+template <bool WRITE>
+StripResult strip_scalar(const uint8_t *buf, size_t a, size_t b, bool in_header, uint8_t *out)
+{
+    size_t o = 0, p = a;
+    while (p < b) {
+        if (in_header) {
+            const uint8_t *nl = (const uint8_t *)memchr(buf + p, '\n', b - p);
+            if (!nl) return {o, SIZE_MAX, true};
+            p = (size_t)(nl - buf) + 1;
+            in_header = false;
+            continue;
+        }
+        size_t q = next_special_scalar(buf, p, b);
+        if (WRITE) memcpy(out + o, buf + p, q - p);
+        o += q - p;
+        if (q == b) break;
+        uint8_t c = buf[q];
+        p = q + 1;
+        if (c == '>') {
+            if (WRITE) out[o] = '>';
+            ++o;
+            in_header = true;
+        } else if (c == 0xFF) {
+            return {o, q, false};
+        }
+    }
+    return {o, SIZE_MAX, in_header};
+}
+
+// AVX2 scan: 32 bytes per step; the common 60-column FASTA line costs two steps.
+template <bool WRITE>
+__attribute__((target("avx2"))) StripResult strip_avx2(const uint8_t *buf, size_t a, size_t b, bool in_header, uint8_t *out)
+{
+    const __m256i v_nl = _mm256_set1_epi8('\n'), v_gt = _mm256_set1_epi8('>'), v_ff = _mm256_set1_epi8((char)0xFF);
+    size_t o = 0, p = a;
+    while (p < b) {
+        if (in_header) {
+            const uint8_t *nl = (const uint8_t *)memchr(buf + p, '\n', b - p);
+            if (!nl) return {o, SIZE_MAX, true};
+            p = (size_t)(nl - buf) + 1;
+            in_header = false;
+            continue;
+        }
+        if (p + 32 <= b) {
+            __m256i v = _mm256_loadu_si256((const __m256i *)(buf + p));
+            __m256i sp = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(v, v_nl), _mm256_cmpeq_epi8(v, v_gt)), _mm256_cmpeq_epi8(v, v_ff));
+            uint32_t m = (uint32_t)_mm256_movemask_epi8(sp);
+            unsigned keep = m ? (unsigned)__builtin_ctz(m) : 32u;
+            if (WRITE) {
+                // the store may run past the kept bytes; the caller guarantees 32 bytes of slack at `out`,
+                // and whatever follows is overwritten by the next step of this same block
+                _mm256_storeu_si256((__m256i *)(out + o), v);
+            }
+            o += keep;
+            if (!m) {
+                p += 32;
+                continue;
+            }
+            uint8_t c = buf[p + keep];
+            size_t q = p + keep;
+            p = q + 1;
+            if (c == '>') {
+                if (WRITE) out[o] = '>';
+                ++o;
+                in_header = true;
+            } else if (c == 0xFF) {
+                return {o, q, false};
+            }
+            continue;
+        }
+        // tail shorter than one vector
+        size_t q = next_special_scalar(buf, p, b);
+        if (WRITE) memcpy(out + o, buf + p, q - p);
+        o += q - p;
+        if (q == b) break;
+        uint8_t c = buf[q];
+        p = q + 1;
+        if (c == '>') {
+            if (WRITE) out[o] = '>';
+            ++o;
+            in_header = true;
+        } else if (c == 0xFF) {
+            return {o, q, false};
+        }
+    }
+    return {o, SIZE_MAX, in_header};
+}
+
+bool have_avx2()
+{
+    static const bool v = __builtin_cpu_supports("avx2");
+    return v;
+}
+
+}  // namespace
+
+// `out` must have room for (b - a) + 32 bytes: the vector path stores whole 32-byte words.
+StripResult strip_block(const uint8_t *buf, size_t a, size_t b, bool in_header, uint8_t *out)
+{
+    return have_avx2() ? strip_avx2<true>(buf, a, b, in_header, out) : strip_scalar<true>(buf, a, b, in_header, out);
+}
+
+StripResult strip_block_count(const uint8_t *buf, size_t a, size_t b, bool in_header)
+{
+    return have_avx2() ? strip_avx2<false>(buf, a, b, in_header, nullptr) : strip_scalar<false>(buf, a, b, in_header, nullptr);
+}
+
+}  // namespace fkb
