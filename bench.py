@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric: Gbases/s counted, k = 11 on a 3.1 Gbp synthetic genome, N B200s.
+
+    python bench.py [--gpus N --steps K --warmup W]            # N > 1: launched by torch.distributed.run
+    python bench.py --impl reference [...]                     # the reference's own CPU implementation
+
+One "step" = one pass of the counting hot path over the whole workload (config 4 of BASELINE.json:
+3.1e9 bases, 24 records, 60-column FASTA, k = 11):
+    value : stripped stream already resident in HBM -> zero accumulators, count kernel(s), [NCCL reduce],
+            finalize (N, base counts, node count); timed with CUDA events, max over ranks.
+    e2e   : the same job through the host-buffer C-ABI call -- raw FASTA bytes in PINNED HOST memory ->
+            host strip threads -> H2D -> kernels -> [reduce] -> finalize -> table + counts back on the host.
+Strong scaling: the 3.1 Gbp are split into N contiguous shards (16-byte halo), one per GPU; per-GPU tables
+are summed with one NCCL reduce (plus a max-reduce of the prefix flags and a sum of 12 scalars).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "Gbases/s counted, k=11 on 3.1 Gbp"
+UNIT = "Gbases/s"
+N_BASES = 3_100_000_000
+K = 11
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi DURING the timed region
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.samples = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.samples.append(parts)
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for p in self.samples:
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# the reference arm: the reference's own CPU implementation on a bounded sample of the workload
+# --------------------------------------------------------------------------------------------------
+def reference_sample_run(sample_bases: int, k: int, workdir: str):
+    """Run the untouched reference binary (oracle/_ref/findKmer) on a `sample_bases` file of the workload's
+    shape; returns (count-phase seconds, total seconds, kind).  Falls back to the C port of the oracle only when
+    the binary is absent."""
+    from findkmer_b200 import synth
+    from oracle import harness
+    lay = synth.config4(n_bases=sample_bases)
+    data = synth.render(lay)
+    if harness.reference_available():
+        # -z with a huge threshold: the count phase is identical, the CSV stays header-only (the launcher's own
+        # runs use -z 1000 on the full genome, k6thru11fullANDupstream.sh:21-24)
+        r = harness.run_reference(data, k, z=1000000, probe=False, time_phases=True, timeout=1800)
+        if not r.ok or r.count_seconds is None:
+            raise RuntimeError("reference run failed: " + r.stdout[-400:])
+        return r.count_seconds, r.total_seconds, "reference"
+    t0 = time.perf_counter()
+    o = harness.oracle_count_fasta(data, k)
+    dt = time.perf_counter() - t0
+    assert o.rc == 0
+    return dt, dt, "port"
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sample = args.ref_sample_bases
+    times = []
+    kind = "reference"
+    with tempfile.TemporaryDirectory() as d:
+        for i in range(args.warmup + args.steps):
+            cs, ts, kind = reference_sample_run(sample, args.k, d)
+            if i >= args.warmup:
+                times.append(cs)
+    mean_s = sum(times) / len(times)
+    value = sample / mean_s / 1e9
+    cores = 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": mean_s * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": workload_config(args, extra={"sample": f"first-principles sample: {sample} bases of the same shape per step"}),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{sample} bases (config-4 shape, 24 records, 60-col), k={args.k}, count phase only, "
+                                   f"single-threaded reference on {os.cpu_count()} host cores"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, extra=None):
+    cfg = {"workload": f"config 4: synthetic {args.bases / 1e9:.3g} Gbp genome, 24 records, 60-column FASTA, k={args.k} (4^{args.k}-entry uint32 table)",
+           "k": args.k, "n_bases": args.bases, "records": 24, "line_width": 60, "seed": 20144,
+           "l2": "inputs exceed L2 (3.1 GB stream per pass vs 126 MB L2); no flush needed",
+           "sharding": f"{args.gpus} contiguous shard(s), 16-byte left halo, NCCL sum-reduce of per-GPU tables" if args.gpus > 1 else "1 shard"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def shard_cuts(total: int, world: int):
+    """contiguous byte ranges with 16-byte aligned cut points"""
+    cuts = [((total * r // world) + 15) // 16 * 16 for r in range(world)] + [total]
+    cuts[0] = 0
+    return cuts
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--bases", type=int, default=N_BASES, help="workload size (default: the metric's 3.1e9)")
+    ap.add_argument("--k", type=int, default=K)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample-bases", type=int, default=20_000_000, help="bounded sample for the cpu_baseline leg")
+    ap.add_argument("--ref-sample-bases", type=int, default=4_000_000, help="per-step sample of --impl reference")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from findkmer_b200 import synth
+    from findkmer_b200.engine import KmerCounter
+    from findkmer_b200._lib import FkbCounts
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            print(f"bench.py: --gpus {args.gpus} needs torch.distributed.run with {args.gpus} ranks", file=sys.stderr)
+            return 2
+        args.gpus = world
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    counter = KmerCounter(local_rank)
+    k = args.k
+    raw_lay = synth.config4(n_bases=args.bases)
+    str_lay = raw_lay.stripped()
+    stream_total = str_lay.total_bytes
+    raw_total = raw_lay.total_bytes
+
+    # ---- device-resident shard of the stripped stream (value leg) ----
+    cuts = shard_cuts(stream_total, world)
+    b, e = cuts[rank], cuts[rank + 1]
+    halo = 16 if rank > 0 else 0
+    d_stream = counter.synth_fasta_device(str_lay, b - halo, e - b + halo)
+    acc = counter.new_accumulators(k)
+    torch.cuda.synchronize()
+    lib, ctx = counter._lib, counter._ctx
+    st = torch.cuda.current_stream(dev)
+    d_counts = torch.zeros(12, dtype=torch.int64, device=dev)
+    import ctypes
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_acc():
+        if world > 1:
+            dist.reduce(acc.table, 0, op=dist.ReduceOp.SUM)
+            dist.reduce(acc.flags, 0, op=dist.ReduceOp.MAX)
+            dist.reduce(acc.partials, 0, op=dist.ReduceOp.SUM)
+
+    ev_pairs = []
+
+    def value_step(record: bool):
+        counter._check(lib.fkb_zero_device(ctx, k, acc.table.data_ptr(), acc.flags.data_ptr(), acc.partials.data_ptr(), st.cuda_stream))
+        if record:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+        counter.count_stream_device(d_stream, k, acc, halo, d_stream.numel())
+        if record:
+            e1.record(st)
+            ev_pairs.append((e0, e1))
+        reduce_acc()
+        if rank == 0:
+            counter._check(lib.fkb_finalize_device(ctx, k, acc.table.data_ptr(), acc.flags.data_ptr(), acc.partials.data_ptr(),
+                                                   stream_total, d_counts.data_ptr(), st.cuda_stream))
+
+    for _ in range(args.warmup):
+        value_step(False)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = counter.launches
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record(st)
+    for _ in range(args.steps):
+        value_step(True)
+    t_end.record(st)
+    barrier()
+    launches = counter.launches - launches0
+    clock_info = clocks.stop() if rank == 0 else None
+    total_ms = t_start.elapsed_time(t_end)
+    kernel_ms = sum(a.elapsed_time(b_) for a, b_ in ev_pairs) / len(ev_pairs)
+    if world > 1:
+        t = torch.tensor([total_ms, kernel_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, kernel_ms = float(t[0]), float(t[1])
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt[0])
+    ms_per_step = total_ms / args.steps
+    value = args.bases / (ms_per_step * 1e-3) / 1e9
+
+    # sanity of what was timed (rank 0): conservation over the record layout
+    if rank == 0:
+        c = FkbCounts.from_buffer_copy(d_counts.cpu().numpy().tobytes())
+        expect = sum(max(0, raw_lay.record_bases(r) - k + 1) for r in range(raw_lay.n_records))
+        assert c.n_kmers == expect and c.base_total == args.bases and not c.rollover, (c.n_kmers, expect, c.base_total)
+
+    # ---- roofline of the dominant kernel (count): algorithmic bytes = 1 B/base of stream + the 4^k x 4 B table ----
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    shard_bytes = (e - b) + (4 ** k) * 4  # per launch (per rank): this rank's stream bytes + its table
+    achieved = shard_bytes / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "count (fused encode + table update)", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": shard_bytes,
+                "peak_source": peak_src}
+
+    # ---- e2e leg: raw FASTA bytes in pinned host memory -> counts on the host ----
+    e2e = None
+    if not args.no_e2e:
+        rcuts = shard_cuts(raw_total, world)
+        ra, rb = rcuts[rank], rcuts[rank + 1]
+        look = min(ra, 1 << 16)
+        d_raw = counter.synth_fasta_device(raw_lay, ra - look, rb - ra + look)
+        h_raw = torch.empty(d_raw.numel(), dtype=torch.uint8, pin_memory=True)
+        h_raw.copy_(d_raw)
+        torch.cuda.synchronize()
+        del d_raw, d_stream
+        torch.cuda.empty_cache()
+        h_table = torch.empty(4 ** k, dtype=torch.int32, pin_memory=True)
+        h_counts = FkbCounts()
+        h2d = d2h = 0
+
+        def e2e_step():
+            nonlocal h2d, d2h
+            if world == 1:
+                counter._check(lib.fkb_count_fasta_host(ctx, h_raw.data_ptr(), h_raw.numel(), k, h_table.data_ptr(), ctypes.byref(h_counts)))
+                h2d = h_counts.stream_bytes + 16
+                d2h = h_table.numel() * 4 + ctypes.sizeof(FkbCounts)
+                return
+            counter._check(lib.fkb_zero_device(ctx, k, acc.table.data_ptr(), acc.flags.data_ptr(), acc.partials.data_ptr(), st.cuda_stream))
+            torch.cuda.synchronize()
+            sb, stop, eih = counter.count_fasta_range(h_raw, look, k, acc)
+            h2d = sb + 16
+            reduce_acc()
+            if rank == 0:
+                counter._check(lib.fkb_finalize_device(ctx, k, acc.table.data_ptr(), acc.flags.data_ptr(), acc.partials.data_ptr(),
+                                                       stream_total, d_counts.data_ptr(), st.cuda_stream))
+                h_table.copy_(acc.table, non_blocking=True)
+                hc = d_counts.cpu()
+                ctypes.memmove(ctypes.byref(h_counts), hc.numpy().ctypes.data, ctypes.sizeof(FkbCounts))
+                d2h = h_table.numel() * 4 + ctypes.sizeof(FkbCounts)
+            torch.cuda.synchronize()
+
+        e2e_step()  # warm-up (allocates the pipeline's device stream and pinned slots)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+        if world > 1:
+            t = torch.tensor([e2e_s, float(h2d)], dtype=torch.float64, device=dev)
+            tm = t.clone()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            e2e_s, h2d = float(tm[0]), int(t[1])
+        if rank == 0:
+            assert h_counts.n_kmers == expect and h_counts.base_total == args.bases
+            assert int(h_table.to(torch.int64).sum()) == expect
+        e2e = {"value": args.bases / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps,
+               "path": "pinned host FASTA bytes -> host strip threads -> H2D -> count -> finalize -> table+counts D2H"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        with tempfile.TemporaryDirectory() as d:
+            cs, ts, kind = reference_sample_run(args.cpu_sample_bases, k, d)
+        cpu_baseline = {"value": args.cpu_sample_bases / cs / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
+                        "sample": f"{args.cpu_sample_bases} bases of the same shape (24 records, 60-col), k={k}; count phase {cs:.2f} s "
+                                  f"(whole run {ts:.2f} s); the reference is single-threaded; host has {os.cpu_count()} cores"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
+                "data": "synthetic", "config": workload_config(args), "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_info}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    counter.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -29,7 +29,7 @@ EXPORTS = [
     "fkb_create", "fkb_destroy", "fkb_last_error", "fkb_status_string", "fkb_version", "fkb_device_info",
     "fkb_strip_fasta", "fkb_alloc_pinned", "fkb_free_pinned",
     "fkb_table_entries", "fkb_prefix_flags_bytes", "fkb_zero_device", "fkb_count_stream_device", "fkb_finalize_device",
-    "fkb_count_fasta_host", "fkb_count_stream_host", "fkb_count_file",
+    "fkb_count_fasta_host", "fkb_count_stream_host", "fkb_count_fasta_host_range", "fkb_count_file",
     "fkb_write_base_stats", "fkb_write_histogram", "fkb_max_nodes",
     "fkb_synth_fasta_device", "fkb_launch_count",
 ]
@@ -120,8 +120,11 @@ def load() -> ctypes.CDLL:
     lib.fkb_write_histogram.restype = c_int
     lib.fkb_max_nodes.argtypes = [c_int]
     lib.fkb_max_nodes.restype = c_uint64
-    lib.fkb_synth_fasta_device.argtypes = [ctx, c_void_p, c_uint64, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_uint64,
-                                           c_int, c_int, c_void_p]
+    lib.fkb_synth_fasta_device.argtypes = [ctx, c_void_p, c_uint64, c_uint64, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                           c_uint64, c_int, c_int, c_void_p]
+    lib.fkb_count_fasta_host_range.argtypes = [ctx, c_void_p, c_size_t, c_size_t, c_int, c_void_p, c_void_p, c_void_p,
+                                               POINTER(c_uint64), POINTER(c_uint64), POINTER(c_int)]
+    lib.fkb_count_fasta_host_range.restype = c_int
     lib.fkb_synth_fasta_device.restype = c_int
     lib.fkb_launch_count.argtypes = [ctx]
     lib.fkb_launch_count.restype = c_uint64

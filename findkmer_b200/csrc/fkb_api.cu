@@ -150,6 +150,154 @@ int finish_host(fkb_context *ctx, int k, uint64_t stream_bytes, uint32_t *table,
 
 }  // namespace
 
+// Loader pipeline over buf[own_offset, len): host threads strip 4 MiB blocks into pinned slots; this thread
+// commits the blocks IN ORDER -- H2D copy to the running offset in the device stream, then a count kernel over
+// the newly arrived byte range (its left halo is already there) -- and recycles a slot when its copy is done.
+// Device stream layout: [16 halo bytes][stripped bytes of the owned range]; the halo is the last 16 stripped
+// bytes in front of the shard (zeros = reset bytes at the start of a file).
+static int pipeline_range(fkb_context *ctx, const uint8_t *fasta, size_t len, size_t own_offset, int k, uint32_t *d_table, uint8_t *d_flags,
+                          fkb_partials *d_partials, uint64_t *stream_bytes, uint64_t *stop_offset, int *ends_in_header_out)
+{
+    *stream_bytes = 0;
+    *stop_offset = UINT64_MAX;
+    *ends_in_header_out = 0;
+    if (int s = ensure_stream(ctx, (len - own_offset) + 16 + 64)) return s;
+    if (int s = ensure_slots(ctx)) return s;
+
+    // ---- left halo ----
+    uint8_t halo[16];
+    memset(halo, 0, sizeof halo);
+    if (own_offset > 0) {
+        size_t look = 256;
+        std::vector<uint8_t> tmp;
+        for (;;) {
+            size_t lb = own_offset > look ? own_offset - look : 0;
+            tmp.assign(own_offset - lb + 64, 0);
+            fkb::StripResult r = fkb::strip_block(fasta, lb, own_offset, fkb::in_header_at(fasta, lb), tmp.data());
+            if (r.stop_pos != SIZE_MAX) {  // the scan ended before this shard begins: it owns nothing
+                *stop_offset = r.stop_pos;
+                return FKB_OK;
+            }
+            if (r.n_out >= 16 || lb == 0) {
+                size_t n = r.n_out < 16 ? r.n_out : 16;
+                memcpy(halo + 16 - n, tmp.data() + r.n_out - n, n);
+                break;
+            }
+            look *= 8;
+        }
+    }
+    FKB_CUDA(ctx, cudaMemcpyAsync(ctx->d_stream, halo, 16, cudaMemcpyHostToDevice, ctx->s_pipe));
+    FKB_CUDA(ctx, cudaStreamSynchronize(ctx->s_pipe));  // halo[] is a stack buffer
+
+    const size_t span = len - own_offset;
+    const size_t n_blocks = (span + kBlockBytes - 1) / kBlockBytes;
+    const int n_slots = fkb_context::kSlots;
+    int n_threads = fkb::default_host_threads();
+    if ((size_t)n_threads > n_blocks) n_threads = (int)n_blocks;
+
+    struct Task { fkb::StripResult r; bool done = false; };
+    std::vector<Task> tasks(n_blocks);
+    std::mutex mu;
+    std::condition_variable cv_done, cv_slot;
+    std::atomic<size_t> next{0};
+    size_t released = 0;  // blocks whose H2D copy has completed, in order: their slots may be reused (guarded by mu)
+    bool abort_all = false;
+
+    auto worker = [&] {
+        for (;;) {
+            size_t i = next.fetch_add(1);
+            if (i >= n_blocks) return;
+            {   // slot i % n_slots last held block i - n_slots
+                std::unique_lock<std::mutex> lk(mu);
+                cv_slot.wait(lk, [&] { return abort_all || i < released + (size_t)n_slots; });
+                if (abort_all) return;
+            }
+            size_t a = own_offset + i * kBlockBytes, b = a + kBlockBytes < len ? a + kBlockBytes : len;
+            fkb::StripResult r = fkb::strip_block(fasta, a, b, fkb::in_header_at(fasta, a), ctx->slots[i % n_slots]);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                tasks[i].r = r;
+                tasks[i].done = true;
+            }
+            cv_done.notify_all();
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; ++t) pool.emplace_back(worker);
+
+    size_t dev_off = 16, counted = 16;
+    bool stopped = false, ends_in_header = false;
+    cudaError_t cuda_err = cudaSuccess;
+    const size_t count_every = 32u << 20;  // one count kernel per >= 32 MiB of newly arrived stream
+    auto release_one = [&] {
+        std::lock_guard<std::mutex> lk(mu);
+        ++released;
+        cv_slot.notify_all();
+    };
+    for (size_t i = 0; i < n_blocks && cuda_err == cudaSuccess && !stopped; ++i) {
+        // wait for block i; while waiting, retire finished copies so the workers get their slots back
+        for (;;) {
+            size_t rel;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                if (tasks[i].done) break;
+                rel = released;
+                if (rel >= i) {  // nothing outstanding: the workers cannot be starved of slots
+                    cv_done.wait(lk, [&] { return tasks[i].done; });
+                    break;
+                }
+            }
+            cuda_err = cudaEventSynchronize(ctx->slot_free[rel % n_slots]);
+            if (cuda_err != cudaSuccess) break;
+            release_one();
+        }
+        if (cuda_err != cudaSuccess) break;
+        const fkb::StripResult r = tasks[i].r;
+        const int slot = (int)(i % n_slots);
+        if (r.n_out) {
+            cuda_err = cudaMemcpyAsync(ctx->d_stream + dev_off, ctx->slots[slot], r.n_out, cudaMemcpyHostToDevice, ctx->s_pipe);
+            dev_off += r.n_out;
+        }
+        if (cuda_err == cudaSuccess) cuda_err = cudaEventRecord(ctx->slot_free[slot], ctx->s_pipe);
+        ends_in_header = r.ends_in_header;
+        if (r.stop_pos != SIZE_MAX) {  // byte 0xFF outside a header: the reference's loop ends here
+            stopped = true;
+            ends_in_header = false;
+            *stop_offset = r.stop_pos;
+        }
+        const bool last = stopped || i + 1 == n_blocks;
+        if (cuda_err == cudaSuccess && dev_off > counted && (dev_off - counted >= count_every || last)) {
+            int launches = 0;
+            cuda_err = fkb::launch_count(launch_info(ctx), ctx->d_stream, counted, dev_off, k, d_table, d_flags, d_partials,
+                                         ctx->s_pipe, &launches);
+            ctx->launches += launches;
+            counted = dev_off;
+        }
+        while (cuda_err == cudaSuccess) {  // opportunistic retire
+            size_t rel;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                rel = released;
+            }
+            if (rel > i || cudaEventQuery(ctx->slot_free[rel % n_slots]) != cudaSuccess) break;
+            release_one();
+        }
+    }
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        abort_all = true;
+    }
+    cv_slot.notify_all();
+    for (auto &th : pool) th.join();
+    if (cuda_err != cudaSuccess) {
+        cudaStreamSynchronize(ctx->s_pipe);
+        return fail(ctx, FKB_ERR_CUDA, "loader pipeline: %s", cudaGetErrorString(cuda_err));
+    }
+    *stream_bytes = dev_off - 16;
+    *ends_in_header_out = ends_in_header ? 1 : 0;
+    return FKB_OK;
+}
+
 extern "C" {
 
 const char *fkb_version(void) { return "findkmer_b200 0.1 (sm_100a)"; }
@@ -390,6 +538,23 @@ int fkb_count_stream_host(fkb_context *ctx, const uint8_t *stream, size_t len, i
     return finish_host(ctx, k, len, table, counts);
 }
 
+int fkb_count_fasta_host_range(fkb_context *ctx, const uint8_t *buf, size_t len, size_t own_offset, int k, uint32_t *d_table,
+                               uint8_t *d_flags, fkb_partials *d_partials, uint64_t *stream_bytes, uint64_t *stop_offset, int *ends_in_header)
+{
+    if (!ctx || !buf || !d_table || !d_flags || !d_partials || !stream_bytes || !stop_offset || !ends_in_header || own_offset > len)
+        return FKB_ERR_BAD_ARG;
+    if (int s = check_k(ctx, k)) return s;
+    FKB_CUDA(ctx, cudaSetDevice(ctx->device));
+    *stream_bytes = 0;
+    *stop_offset = UINT64_MAX;
+    *ends_in_header = 0;
+    if (own_offset == len) return FKB_OK;
+    int s = pipeline_range(ctx, buf, len, own_offset, k, d_table, d_flags, d_partials, stream_bytes, stop_offset, ends_in_header);
+    cudaError_t e = cudaStreamSynchronize(ctx->s_pipe);  // results are handed to the caller's stream
+    if (s == FKB_OK && e != cudaSuccess) return fail(ctx, FKB_ERR_CUDA, "cudaStreamSynchronize: %s", cudaGetErrorString(e));
+    return s;
+}
+
 int fkb_count_fasta_host(fkb_context *ctx, const uint8_t *fasta, size_t len, int k, uint32_t *table, fkb_counts *counts)
 {
     if (!ctx || !table || !counts || (len && !fasta)) return FKB_ERR_BAD_ARG;
@@ -397,120 +562,18 @@ int fkb_count_fasta_host(fkb_context *ctx, const uint8_t *fasta, size_t len, int
     if (len == 0) return fail(ctx, FKB_ERR_EMPTY_INPUT, "Sequence File Is Empty");
     FKB_CUDA(ctx, cudaSetDevice(ctx->device));
     if (int s = ensure_table(ctx, k)) return s;
-    if (int s = ensure_stream(ctx, len + 64)) return s;
-    if (int s = ensure_slots(ctx)) return s;
     if (int s = fkb_zero_device(ctx, k, ctx->d_table, ctx->d_flags, ctx->d_partials, ctx->s_pipe)) return s;
-
-    // Loader pipeline: host threads strip 4 MiB blocks of the file into pinned slots; this thread commits the
-    // blocks IN ORDER -- H2D copy to the running offset in the device stream, then a count kernel over the
-    // newly arrived byte range (its left halo is already there) -- and recycles the slot when its copy is done.
-    const size_t n_blocks = (len + kBlockBytes - 1) / kBlockBytes;
-    const int n_slots = fkb_context::kSlots;
-    int n_threads = fkb::default_host_threads();
-    if ((size_t)n_threads > n_blocks) n_threads = (int)n_blocks;
-
-    struct Task { fkb::StripResult r; bool done = false; };
-    std::vector<Task> tasks(n_blocks);
-    std::mutex mu;
-    std::condition_variable cv_done, cv_slot;
-    std::atomic<size_t> next{0};
-    size_t released = 0;  // blocks whose H2D copy has completed, in order: their slots may be reused (guarded by mu)
-    bool abort_all = false;
-
-    auto worker = [&] {
-        for (;;) {
-            size_t i = next.fetch_add(1);
-            if (i >= n_blocks) return;
-            {   // slot i % n_slots last held block i - n_slots
-                std::unique_lock<std::mutex> lk(mu);
-                cv_slot.wait(lk, [&] { return abort_all || i < released + (size_t)n_slots; });
-                if (abort_all) return;
-            }
-            size_t a = i * kBlockBytes, b = a + kBlockBytes < len ? a + kBlockBytes : len;
-            fkb::StripResult r = fkb::strip_block(fasta, a, b, fkb::in_header_at(fasta, a), ctx->slots[i % n_slots]);
-            {
-                std::lock_guard<std::mutex> lk(mu);
-                tasks[i].r = r;
-                tasks[i].done = true;
-            }
-            cv_done.notify_all();
-        }
-    };
-    std::vector<std::thread> pool;
-    for (int t = 0; t < n_threads; ++t) pool.emplace_back(worker);
-
-    size_t dev_off = 0, counted = 0;
-    bool stopped = false, ends_in_header = false;
-    cudaError_t cuda_err = cudaSuccess;
-    const size_t count_every = 32u << 20;  // one count kernel per >= 32 MiB of newly arrived stream
-    auto release_one = [&] {
-        std::lock_guard<std::mutex> lk(mu);
-        ++released;
-        cv_slot.notify_all();
-    };
-    for (size_t i = 0; i < n_blocks && cuda_err == cudaSuccess && !stopped; ++i) {
-        // wait for block i; while waiting, retire finished copies so the workers get their slots back
-        for (;;) {
-            size_t rel;
-            {
-                std::unique_lock<std::mutex> lk(mu);
-                if (tasks[i].done) break;
-                rel = released;
-                if (rel >= i) {  // nothing outstanding: the workers cannot be starved of slots
-                    cv_done.wait(lk, [&] { return tasks[i].done; });
-                    break;
-                }
-            }
-            cuda_err = cudaEventSynchronize(ctx->slot_free[rel % n_slots]);
-            if (cuda_err != cudaSuccess) break;
-            release_one();
-        }
-        if (cuda_err != cudaSuccess) break;
-        const fkb::StripResult r = tasks[i].r;
-        const int slot = (int)(i % n_slots);
-        if (r.n_out) {
-            cuda_err = cudaMemcpyAsync(ctx->d_stream + dev_off, ctx->slots[slot], r.n_out, cudaMemcpyHostToDevice, ctx->s_pipe);
-            dev_off += r.n_out;
-        }
-        if (cuda_err == cudaSuccess) cuda_err = cudaEventRecord(ctx->slot_free[slot], ctx->s_pipe);
-        ends_in_header = r.ends_in_header;
-        if (r.stop_pos != SIZE_MAX) {  // byte 0xFF outside a header: the reference's loop ends here
-            stopped = true;
-            ends_in_header = false;
-        }
-        const bool last = stopped || i + 1 == n_blocks;
-        if (cuda_err == cudaSuccess && dev_off > counted && (dev_off - counted >= count_every || last)) {
-            int launches = 0;
-            cuda_err = fkb::launch_count(launch_info(ctx), ctx->d_stream, counted, dev_off, k, ctx->d_table, ctx->d_flags, ctx->d_partials,
-                                         ctx->s_pipe, &launches);
-            ctx->launches += launches;
-            counted = dev_off;
-        }
-        while (cuda_err == cudaSuccess) {  // opportunistic retire
-            size_t rel;
-            {
-                std::lock_guard<std::mutex> lk(mu);
-                rel = released;
-            }
-            if (rel > i || cudaEventQuery(ctx->slot_free[rel % n_slots]) != cudaSuccess) break;
-            release_one();
-        }
-    }
-    {
-        std::lock_guard<std::mutex> lk(mu);
-        abort_all = true;
-    }
-    cv_slot.notify_all();
-    for (auto &th : pool) th.join();
-    if (cuda_err != cudaSuccess) {
+    uint64_t stream_bytes = 0, stop = 0;
+    int ends_in_header = 0;
+    if (int s = pipeline_range(ctx, fasta, len, 0, k, ctx->d_table, ctx->d_flags, ctx->d_partials, &stream_bytes, &stop, &ends_in_header)) {
         cudaStreamSynchronize(ctx->s_pipe);
-        return fail(ctx, FKB_ERR_CUDA, "loader pipeline: %s", cudaGetErrorString(cuda_err));
+        return s;
     }
     if (ends_in_header) {
         cudaStreamSynchronize(ctx->s_pipe);
         return fail(ctx, FKB_ERR_UNTERMINATED_HEADER, "%s", fkb_status_string(FKB_ERR_UNTERMINATED_HEADER));
     }
-    return finish_host(ctx, k, dev_off, table, counts);
+    return finish_host(ctx, k, stream_bytes, table, counts);
 }
 
 int fkb_count_file(fkb_context *ctx, const char *path, int k, uint32_t *table, fkb_counts *counts)
@@ -537,11 +600,11 @@ int fkb_count_file(fkb_context *ctx, const char *path, int k, uint32_t *table, f
 }
 
 // ---- synthetic inputs ----------------------------------------------------------------------------
-int fkb_synth_fasta_device(fkb_context *ctx, uint8_t *d_out, uint64_t total_bytes, int n_records, const uint64_t *rec_offsets,
-                           const uint64_t *rec_base0, const uint8_t *headers, int header_len, int line_width, uint64_t seed,
-                           int n_runs, int soft_mask, void *cuda_stream)
+int fkb_synth_fasta_device(fkb_context *ctx, uint8_t *d_out, uint64_t first_byte, uint64_t n_bytes, int n_records,
+                           const uint64_t *rec_offsets, const uint64_t *rec_base0, const uint8_t *headers, int header_len, int line_width,
+                           uint64_t seed, int n_runs, int soft_mask, void *cuda_stream)
 {
-    if (!ctx || !d_out || !rec_offsets || !rec_base0 || !headers || n_records < 1 || header_len < 2) return FKB_ERR_BAD_ARG;
+    if (!ctx || !d_out || !rec_offsets || !rec_base0 || !headers || n_records < 1 || header_len < 1) return FKB_ERR_BAD_ARG;
     if ((uintptr_t)d_out & 15) return fail(ctx, FKB_ERR_BAD_ARG, "d_out must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)cuda_stream;
     uint64_t *d_off = nullptr, *d_b0 = nullptr;
@@ -554,7 +617,7 @@ int fkb_synth_fasta_device(fkb_context *ctx, uint8_t *d_out, uint64_t total_byte
     FKB_CUDA(ctx, cudaMemcpyAsync(d_b0, rec_base0, nb, cudaMemcpyHostToDevice, st));
     FKB_CUDA(ctx, cudaMemcpyAsync(d_hdr, headers, nh, cudaMemcpyHostToDevice, st));
     int launches = 0;
-    cudaError_t e = fkb::launch_synth(launch_info(ctx), d_out, total_bytes, n_records, d_off, d_b0, d_hdr, header_len, line_width, seed,
+    cudaError_t e = fkb::launch_synth(launch_info(ctx), d_out, first_byte, n_bytes, n_records, d_off, d_b0, d_hdr, header_len, line_width, seed,
                                       n_runs, soft_mask, st, &launches);
     ctx->launches += launches;
     cudaError_t e2 = cudaStreamSynchronize(st);  // the temporaries are freed below

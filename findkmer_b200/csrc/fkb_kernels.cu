@@ -298,16 +298,20 @@ __device__ __forceinline__ uint8_t synth_letter(uint64_t g, uint64_t seed, int n
     return out;
 }
 
-__global__ void __launch_bounds__(kThreads) synth_fasta_kernel(uint8_t *__restrict__ out, uint64_t total_bytes, int n_records,
+// Renders bytes [first_byte, first_byte + n_bytes) of the virtual file into out[0, n_bytes).
+// line_width > 0: wrapped lines; == 0: one unwrapped line per record; < 0: the STRIPPED layout (no newline at
+// all: a record is its header bytes followed by its bases -- with header_len == 1 this is the stream contract).
+__global__ void __launch_bounds__(kThreads) synth_fasta_kernel(uint8_t *__restrict__ out, uint64_t first_byte, uint64_t n_bytes, int n_records,
                                                                const uint64_t *__restrict__ rec_off, const uint64_t *__restrict__ rec_base0,
                                                                const uint8_t *__restrict__ headers, int header_len, int line_width,
                                                                uint64_t seed, int n_runs, int soft_mask)
 {
     // each thread renders 16 consecutive bytes and stores them as one 128-bit word
-    const uint64_t n_groups = (total_bytes + 15) / 16;
+    const uint64_t n_groups = (n_bytes + 15) / 16;
     for (uint64_t gi = (uint64_t)blockIdx.x * kThreads + threadIdx.x; gi < n_groups; gi += (uint64_t)gridDim.x * kThreads) {
         uint32_t w[4] = {0, 0, 0, 0};
-        uint64_t p = gi * 16;
+        uint64_t p = first_byte + gi * 16;
+        const uint64_t p_end = first_byte + n_bytes;
         // record of the first byte by binary search; later bytes advance linearly
         int lo = 0, hi = n_records;  // rec_off[lo] <= p < rec_off[hi]
         while (hi - lo > 1) {
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(kThreads) synth_fasta_kernel(uint8_t *__restri
         }
         int r = lo;
         for (int i = 0; i < 16; ++i, ++p) {
-            if (p >= total_bytes) break;
+            if (p >= p_end) break;
             while (r + 1 < n_records && p >= rec_off[r + 1]) ++r;
             uint64_t o = p - rec_off[r];
             uint8_t ch;
@@ -325,7 +329,9 @@ __global__ void __launch_bounds__(kThreads) synth_fasta_kernel(uint8_t *__restri
             } else {
                 o -= header_len;
                 uint64_t nb = rec_base0[r + 1] - rec_base0[r];
-                if (line_width == 0) {
+                if (line_width < 0) {
+                    ch = synth_letter(rec_base0[r] + o, seed, n_runs, soft_mask);
+                } else if (line_width == 0) {
                     ch = (o == nb) ? (uint8_t)'\n' : synth_letter(rec_base0[r] + o, seed, n_runs, soft_mask);
                 } else {
                     uint64_t q = o / (uint64_t)(line_width + 1), col = o % (uint64_t)(line_width + 1);
@@ -335,10 +341,10 @@ __global__ void __launch_bounds__(kThreads) synth_fasta_kernel(uint8_t *__restri
             }
             w[i >> 2] |= (uint32_t)ch << (8 * (i & 3));
         }
-        if (gi * 16 + 16 <= total_bytes) {
+        if (gi * 16 + 16 <= n_bytes) {
             reinterpret_cast<uint4 *>(out)[gi] = make_uint4(w[0], w[1], w[2], w[3]);
         } else {
-            for (uint64_t i = 0; gi * 16 + i < total_bytes; ++i) out[gi * 16 + i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
+            for (uint64_t i = 0; gi * 16 + i < n_bytes; ++i) out[gi * 16 + i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
         }
     }
 }
@@ -381,13 +387,13 @@ cudaError_t launch_finalize(const LaunchInfo &li, int k, const uint32_t *d_table
     return cudaGetLastError();
 }
 
-cudaError_t launch_synth(const LaunchInfo &li, uint8_t *d_out, uint64_t total_bytes, int n_records, const uint64_t *d_rec_offsets,
-                         const uint64_t *d_rec_base0, const uint8_t *d_headers, int header_len, int line_width, uint64_t seed,
-                         int n_runs, int soft_mask, cudaStream_t st, int *launches)
+cudaError_t launch_synth(const LaunchInfo &li, uint8_t *d_out, uint64_t first_byte, uint64_t n_bytes, int n_records,
+                         const uint64_t *d_rec_offsets, const uint64_t *d_rec_base0, const uint8_t *d_headers, int header_len, int line_width,
+                         uint64_t seed, int n_runs, int soft_mask, cudaStream_t st, int *launches)
 {
-    if (total_bytes == 0) return cudaSuccess;
-    synth_fasta_kernel<<<grid_for((total_bytes + 15) / 16, li.sm_count, 8), kThreads, 0, st>>>(
-        d_out, total_bytes, n_records, d_rec_offsets, d_rec_base0, d_headers, header_len, line_width, seed, n_runs, soft_mask);
+    if (n_bytes == 0) return cudaSuccess;
+    synth_fasta_kernel<<<grid_for((n_bytes + 15) / 16, li.sm_count, 8), kThreads, 0, st>>>(
+        d_out, first_byte, n_bytes, n_records, d_rec_offsets, d_rec_base0, d_headers, header_len, line_width, seed, n_runs, soft_mask);
     if (launches) ++*launches;
     return cudaGetLastError();
 }

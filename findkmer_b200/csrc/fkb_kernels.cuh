@@ -26,7 +26,7 @@ cudaError_t launch_finalize(const LaunchInfo &li, int k, const uint32_t *d_table
                             const fkb_partials *d_partials, uint64_t stream_bytes, fkb_counts *d_counts,
                             unsigned long long *d_scratch, cudaStream_t st, int *launches);
 
-cudaError_t launch_synth(const LaunchInfo &li, uint8_t *d_out, uint64_t total_bytes, int n_records,
+cudaError_t launch_synth(const LaunchInfo &li, uint8_t *d_out, uint64_t first_byte, uint64_t n_bytes, int n_records,
                          const uint64_t *d_rec_offsets, const uint64_t *d_rec_base0, const uint8_t *d_headers,
                          int header_len, int line_width, uint64_t seed, int n_runs, int soft_mask,
                          cudaStream_t st, int *launches);

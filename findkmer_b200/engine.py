@@ -203,18 +203,30 @@ class KmerCounter:
         return KmerCounts.from_struct(acc.k, table, c)
 
     # -- synthetic inputs in HBM --------------------------------------------------------------------
-    def synth_fasta_device(self, layout):
-        """Render a findkmer_b200.synth.FastaLayout directly in HBM (bit-identical to synth.render)."""
+    def synth_fasta_device(self, layout, first_byte: int = 0, n_bytes: Optional[int] = None):
+        """Render bytes [first_byte, first_byte+n_bytes) of a findkmer_b200.synth.FastaLayout directly in HBM
+        (bit-identical to synth.render).  Returns a torch uint8 CUDA tensor (16-byte aligned storage)."""
         import torch
         offs, base0 = layout.record_offsets()
         total = int(offs[-1])
-        out = torch.empty(total + 64, dtype=torch.uint8, device=torch.device("cuda", self.device))
+        n_bytes = total - first_byte if n_bytes is None else n_bytes
+        assert 0 <= first_byte and first_byte + n_bytes <= total
+        out = torch.empty(n_bytes + 64, dtype=torch.uint8, device=torch.device("cuda", self.device))
         headers = np.frombuffer(b"".join(layout.header(r) for r in range(layout.n_records)), dtype=np.uint8)
         st = torch.cuda.current_stream(out.device).cuda_stream
-        self._check(self._lib.fkb_synth_fasta_device(self._ctx, out.data_ptr(), total, layout.n_records, offs.ctypes.data,
+        self._check(self._lib.fkb_synth_fasta_device(self._ctx, out.data_ptr(), first_byte, n_bytes, layout.n_records, offs.ctypes.data,
                                                      base0.ctypes.data, headers.ctypes.data, layout.header_len, layout.line_width,
                                                      layout.seed & ((1 << 64) - 1), int(layout.n_runs), int(layout.soft_mask), st))
-        return out[:total]
+        return out[:n_bytes]
+
+    def count_fasta_range(self, data, own_offset: int, k: int, acc: DeviceAccumulators):
+        """One shard of a file (multi-GPU): data = raw bytes with `own_offset` bytes of look-back context in front.
+        Accumulates into `acc`; returns (stream_bytes, stop_offset or None, ends_in_header)."""
+        addr, n, keep = _host_view(data)
+        sb, stop, eih = ctypes.c_uint64(0), ctypes.c_uint64(0), ctypes.c_int(0)
+        self._check(self._lib.fkb_count_fasta_host_range(self._ctx, addr, n, own_offset, k, acc.table.data_ptr(), acc.flags.data_ptr(),
+                                                         acc.partials.data_ptr(), ctypes.byref(sb), ctypes.byref(stop), ctypes.byref(eih)))
+        return sb.value, (None if stop.value == (1 << 64) - 1 else stop.value), bool(eih.value)
 
 
 # ------------------------------------------------------------------------------------------------

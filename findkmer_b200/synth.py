@@ -44,14 +44,14 @@ class FastaLayout:
     """Byte layout of a synthetic multi-record file."""
     n_bases: int
     n_records: int
-    line_width: int          # 0 = one unwrapped line per record
+    line_width: int          # > 0 wrapped; 0 = one unwrapped line per record; < 0 = stripped layout (no newlines)
     header_fmt: str          # must render to the same width for every record index
     seed: int
     n_runs: bool = False     # config 5: N runs
     soft_mask: bool = False  # config 5: lower-case runs
 
     def header(self, r: int) -> bytes:
-        return (self.header_fmt % r).encode("ascii")
+        return (self.header_fmt % r).encode("ascii") if "%" in self.header_fmt else self.header_fmt.encode("ascii")
 
     @property
     def header_len(self) -> int:
@@ -61,7 +61,14 @@ class FastaLayout:
         per = self.n_bases // self.n_records
         return per if r < self.n_records - 1 else self.n_bases - per * (self.n_records - 1)
 
+    def stripped(self) -> "FastaLayout":
+        """The layout of the stream the host loader produces from this file: '>' + bases per record."""
+        from dataclasses import replace
+        return replace(self, line_width=-1, header_fmt=">")
+
     def body_len(self, nb: int) -> int:
+        if self.line_width < 0:
+            return nb
         if self.line_width == 0:
             return nb + 1
         return nb + (nb + self.line_width - 1) // self.line_width
@@ -115,12 +122,14 @@ def render(layout: FastaLayout) -> np.ndarray:
     for r in range(layout.n_records):
         o = int(offs[r])
         hdr = layout.header(r)
-        assert len(hdr) == H and hdr.endswith(b"\n") and hdr.startswith(b">")
+        assert len(hdr) == H and hdr.startswith(b">") and (W < 0 or hdr.endswith(b"\n"))
         out[o:o + H] = np.frombuffer(hdr, dtype=np.uint8)
         nb = layout.record_bases(r)
         body = out[o + H:o + H + layout.body_len(nb)]
         letters = base_letters(layout, np.arange(nb, dtype=np.uint64) + base0[r])
-        if W == 0:
+        if W < 0:
+            body[:] = letters
+        elif W == 0:
             body[:nb] = letters
             body[nb] = 10
         else:
@@ -132,15 +141,7 @@ def render(layout: FastaLayout) -> np.ndarray:
 
 def stripped_stream(layout: FastaLayout) -> np.ndarray:
     """The stream the host loader must produce from render(layout): one '>' per header, no newlines."""
-    offs, base0 = layout.record_offsets()
-    out = np.empty(layout.n_bases + layout.n_records, dtype=np.uint8)
-    o = 0
-    for r in range(layout.n_records):
-        out[o] = ord(">")
-        nb = layout.record_bases(r)
-        out[o + 1:o + 1 + nb] = base_letters(layout, np.arange(nb, dtype=np.uint64) + base0[r])
-        o += nb + 1
-    return out
+    return render(layout.stripped())
 
 
 # ------------------------------------------------------------------------------------------------

@@ -127,6 +127,14 @@ int fkb_count_fasta_host(fkb_context *ctx, const uint8_t *fasta, size_t len, int
 /* same, for an already stripped stream held on the host */
 int fkb_count_stream_host(fkb_context *ctx, const uint8_t *stream, size_t len, int k, uint32_t *table,
                           fkb_counts *counts);
+/* One shard of a file, for multi-GPU runs.  buf[0,len) holds raw file bytes; the shard OWNS buf[own_offset,len)
+ * and buf[0,own_offset) is look-back context (it must reach back to a '\n' or to the start of the file, and
+ * far enough to hold 16 sequence bytes).  Results are ACCUMULATED into the caller's device buffers (to be
+ * reduced across GPUs and then passed to fkb_finalize_device).  stop_offset: offset in buf of a byte 0xFF that
+ * ended the scan, or UINT64_MAX.  ends_in_header: the shard ends inside a '>' line (an error only at end of file). */
+int fkb_count_fasta_host_range(fkb_context *ctx, const uint8_t *buf, size_t len, size_t own_offset, int k,
+                               uint32_t *d_table, uint8_t *d_flags, fkb_partials *d_partials,
+                               uint64_t *stream_bytes, uint64_t *stop_offset, int *ends_in_header);
 /* same, reading the file itself: the reference's `-p <file>` (:416-428, :344) */
 int fkb_count_file(fkb_context *ctx, const char *path, int k, uint32_t *table, fkb_counts *counts);
 
@@ -141,9 +149,12 @@ int fkb_write_histogram(FILE *csv_out, int k, const uint32_t *table, const fkb_c
 uint64_t fkb_max_nodes(int k);
 
 /* ---- synthetic inputs of the BASELINE.json shapes, generated in HBM (bench only) --------------
- * Bit-identical to findkmer_b200/synth.py::render().  rec_offsets/rec_base0: uint64[n_records+1]
+ * Renders bytes [first_byte, first_byte + n_bytes) of the virtual file into d_out[0, n_bytes);
+ * bit-identical to findkmer_b200/synth.py::render().  line_width > 0: wrapped lines, 0: one
+ * unwrapped line per record, < 0: the stripped layout (no newlines; with header_len == 1 and
+ * header ">" this IS the stream contract's output).  rec_offsets/rec_base0: uint64[n_records+1]
  * on the HOST; headers: n_records * header_len bytes on the HOST. */
-int fkb_synth_fasta_device(fkb_context *ctx, uint8_t *d_out, uint64_t total_bytes, int n_records,
+int fkb_synth_fasta_device(fkb_context *ctx, uint8_t *d_out, uint64_t first_byte, uint64_t n_bytes, int n_records,
                            const uint64_t *rec_offsets, const uint64_t *rec_base0, const uint8_t *headers,
                            int header_len, int line_width, uint64_t seed, int n_runs, int soft_mask,
                            void *cuda_stream);

@@ -1,0 +1,257 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the committed golden vectors.
+Every test here needs a real B200: run with `pytest -m gpu`."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_DIR, assert_counts_equal, random_fasta
+
+pytestmark = pytest.mark.gpu
+
+
+def _device_count(counter, stream_np, k, begin=0, end=None, pieces=1):
+    """device-resident path: upload a stripped stream, count [begin,end) in `pieces` launches, finalize"""
+    import torch
+    n = len(stream_np)
+    d = torch.zeros(n + 64, dtype=torch.uint8, device="cuda")
+    d[:n] = torch.from_numpy(np.ascontiguousarray(stream_np))
+    acc = counter.new_accumulators(k)
+    end = n if end is None else end
+    cuts = np.linspace(begin, end, pieces + 1).astype(np.int64)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        counter.count_stream_device(d[:n], k, acc, int(a), int(b))
+    return counter.finalize_device(acc, n), acc
+
+
+# ---- config 1: the reference's own fixture ---------------------------------------------------------
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14])
+def test_test_txt_all_k(counter, harness, test_txt, k):
+    want = harness.oracle_count_fasta(test_txt, k)
+    got = counter.count_fasta(test_txt, k)
+    assert_counts_equal(got, want)
+
+
+def test_k16_device_path_against_golden(counter, golden, test_txt):
+    """k = 16 (the full 32-bit rolling register; 16 GiB table stays in HBM): scalars and sparsity vs the reference run"""
+    import torch
+    g = golden["test_txt"]["16"]
+    stream = counter.strip(test_txt)
+    d = torch.zeros(len(stream) + 64, dtype=torch.uint8, device="cuda")
+    d[:len(stream)] = torch.from_numpy(stream.copy())
+    acc = counter.new_accumulators(16)
+    counter.count_stream_device(d[:len(stream)], 16, acc)
+    got = counter.finalize_device(acc, len(stream), fetch_table=False)
+    assert (got.n_kmers, list(got.base_count), got.base_total, got.node_count) == (g["n_kmers"], g["base_count"], g["base_total"], g["node_count"])
+    assert int(torch.count_nonzero(acc.table)) == g["distinct"] and int(acc.table.sum(dtype=torch.int64)) == g["n_kmers"]
+    del acc, d
+    torch.cuda.empty_cache()
+
+
+def test_test_txt_golden_numbers(counter, golden, test_txt):
+    for key, g in golden["test_txt"].items():
+        if "_z" in key or int(key) > 14:
+            continue
+        got = counter.count_fasta(test_txt, int(key))
+        assert (got.n_kmers, int(np.count_nonzero(got.table)), list(got.base_count), got.base_total, got.node_count) == \
+               (g["n_kmers"], g["distinct"], g["base_count"], g["base_total"], g["node_count"])
+
+
+def test_csv_and_stats_bytes_from_gpu_counts(counter, golden, test_txt, tmp_path):
+    """file -> GPU counts -> host writer must reproduce the reference's files byte for byte"""
+    from findkmer_b200.engine import write_outputs
+    for k, z, name in [(6, None, "6mer_Historam_Of_test.txt.csv"), (11, None, "11mer_Historam_Of_test.txt.csv"),
+                       (6, 1, "6mer_Historam_Of_test.txtzScoreFiltered_z1.csv"), (6, 2, "6mer_Historam_Of_test.txtzScoreFiltered_z2.csv")]:
+        got = counter.count_fasta(test_txt, k)
+        csv, stats = tmp_path / "out.csv", tmp_path / "out.txt"
+        assert write_outputs(got, csv, stats, z_threshold=z) == 0
+        assert csv.read_bytes() == (GOLDEN_DIR / name).read_bytes()
+        assert stats.read_bytes() == (GOLDEN_DIR / f"{k}mer_Base_Stats_Of_test.txt.txt").read_bytes()
+    for k in (1, 3, 7, 8, 9, 10):
+        got = counter.count_fasta(test_txt, k)
+        csv, stats = tmp_path / "o.csv", tmp_path / "o.txt"
+        write_outputs(got, csv, stats)
+        assert hashlib.sha256(csv.read_bytes()).hexdigest() == golden["test_txt"][str(k)]["csv_sha256"]
+        assert hashlib.sha256(stats.read_bytes()).hexdigest() == golden["test_txt"][str(k)]["stats_sha256"]
+
+
+# ---- reset rules ---------------------------------------------------------------------------------
+def test_micro_vectors(counter, harness, golden):
+    from findkmer_b200 import FindKmerError, _lib
+    for rec in golden["micro"]:
+        data = rec["input_latin1"].encode("latin1")
+        k = rec["k"]
+        if rec["hung"]:
+            with pytest.raises(FindKmerError) as e:
+                counter.count_fasta(data, k)
+            assert e.value.status == _lib.FKB_ERR_UNTERMINATED_HEADER
+            continue
+        if data == b"":
+            with pytest.raises(FindKmerError) as e:
+                counter.count_fasta(data, k)
+            assert e.value.status == _lib.FKB_ERR_EMPTY_INPUT
+            continue
+        got = counter.count_fasta(data, k)
+        assert got.node_count == rec["node_count"], rec
+        if rec["ok"]:
+            assert [[int(i), int(got.table[i])] for i in np.flatnonzero(got.table)] == rec["table_nonzero"], rec
+            assert got.base_total == rec["base_total"] and list(got.base_count) == rec["base_count"], rec
+        assert_counts_equal(got, harness.oracle_count_fasta(data, k))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_junk_inputs(counter, harness, golden, seed):
+    recs = [r for r in golden["random"] if r["seed"] == seed]
+    data = random_fasta(seed, recs[0]["n"])
+    for rec in recs:
+        got = counter.count_fasta(data, rec["k"])
+        assert hashlib.sha256(got.table.tobytes()).hexdigest() == rec["table_sha256"]
+        assert (got.n_kmers, got.node_count, list(got.base_count), got.base_total) == \
+               (rec["n_kmers"], rec["node_count"], rec["base_count"], rec["base_total"])
+    for k in (4, 11, 13):
+        assert_counts_equal(counter.count_fasta(data, k), harness.oracle_count_fasta(data, k))
+
+
+def test_ragged_sizes_and_alignments(counter, harness):
+    """every stream length 0..200 and every begin offset: chunk edges, halos, tails"""
+    rng = np.random.default_rng(5)
+    base = np.frombuffer(b"ACGTACGTACGTNACGT>acgt", dtype=np.uint8)[rng.integers(0, 22, size=400)]
+    for n in list(range(0, 70)) + [127, 128, 129, 191, 192, 193, 255, 256, 257, 400]:
+        s = base[:n]
+        for k in (1, 5, 12):
+            want = harness.oracle_count_stream(s, k)
+            got = counter.count_stream(s, k)
+            assert_counts_equal(got, want)
+
+
+def test_device_ranges_compose(counter, harness):
+    """sharding rule: a window belongs to the range that owns its LAST byte; ranges add up exactly"""
+    data = random_fasta(11, 50000)
+    stream = counter.strip(data)
+    for k in (3, 11, 13):
+        want = harness.oracle_count_stream(stream, k)
+        for pieces in (1, 2, 7, 64):
+            got, _ = _device_count(counter, stream, k, pieces=pieces)
+            assert_counts_equal(got, want)
+    # two "ranks" on one GPU: separate accumulators, then the reduction the NCCL path performs
+    import torch
+    k = 9
+    n = len(stream)
+    mid = n // 2 + 3
+    _, acc0 = _device_count(counter, stream, k, 0, mid)
+    _, acc1 = _device_count(counter, stream, k, mid, n)
+    acc0.table += acc1.table
+    acc0.flags = torch.maximum(acc0.flags, acc1.flags)
+    acc0.partials += acc1.partials
+    assert_counts_equal(counter.finalize_device(acc0, n), harness.oracle_count_stream(stream, k))
+
+
+# ---- configs 2, 3 and a slice of 5: k = 6..11 ---------------------------------------------------------
+@pytest.mark.parametrize("k", [6, 7, 8, 9, 10, 11])
+def test_config2_yeast_scale(counter, harness, k):
+    from findkmer_b200 import synth
+    data = synth.render(synth.config2())
+    want = harness.oracle_count_fasta(data, k)
+    assert_counts_equal(counter.count_fasta(data, k), want)
+
+
+@pytest.mark.parametrize("k", [6, 7, 8, 9, 10, 11])
+def test_config3_upstream_records(counter, harness, k):
+    from findkmer_b200 import synth
+    data = synth.render(synth.config3())
+    assert_counts_equal(counter.count_fasta(data, k), harness.oracle_count_fasta(data, k))
+
+
+@pytest.mark.parametrize("k", [8, 11])
+def test_config5_shape_n_runs_and_soft_mask(counter, harness, k):
+    from findkmer_b200 import synth
+    data = synth.render(synth.config5(n_bases=6_000_000))
+    assert_counts_equal(counter.count_fasta(data, k), harness.oracle_count_fasta(data, k))
+
+
+def test_reference_binary_live(counter, harness):
+    """the untouched reference binary travels to the GPU box prebuilt: compare against it directly"""
+    if not harness.reference_available():
+        pytest.skip("oracle/_ref/findKmer not present")
+    from findkmer_b200 import synth
+    data = synth.render(synth.config2(n_bases=600_000))
+    for k in (6, 11):
+        r = harness.run_reference(data, k)
+        got = counter.count_fasta(data, k)
+        assert r.ok
+        assert np.array_equal(harness.csv_to_table(r.csv, k), got.table)
+        assert (r.node_count, r.base_count, r.base_total) == (got.node_count, tuple(got.base_count), got.base_total)
+
+
+# ---- loader / generator twins ---------------------------------------------------------------------------
+def test_device_generator_is_bit_identical_to_numpy(counter):
+    from findkmer_b200 import synth
+    for lay in (synth.config2(n_bases=300_007), synth.config3(n_records=300), synth.config5(n_bases=250_000),
+                synth.config5(n_bases=250_000).stripped()):
+        want = synth.render(lay)
+        got = counter.synth_fasta_device(lay).cpu().numpy()
+        assert np.array_equal(got, want)
+        a, n = 12345, 70001
+        assert np.array_equal(counter.synth_fasta_device(lay, a, n).cpu().numpy(), want[a:a + n])
+
+
+def test_host_pipeline_multi_block_and_eof_alias(counter, harness):
+    """> 4 MiB inputs exercise the block pipeline; a 0xFF byte outside a header ends the scan (EOF aliasing)"""
+    from findkmer_b200 import synth
+    data = synth.render(synth.config2(n_bases=9_000_000)).copy()
+    want = harness.oracle_count_fasta(data, 10)
+    assert_counts_equal(counter.count_fasta(data, 10), want)
+    data[5_000_000] = 0xFF
+    want = harness.oracle_count_fasta(data, 10)
+    assert want.bytes_read == 5_000_001
+    assert_counts_equal(counter.count_fasta(data, 10), want)
+
+
+def test_count_file_and_range_shards(counter, harness, tmp_path):
+    from findkmer_b200 import synth
+    data = synth.render(synth.config5(n_bases=3_000_000))
+    p = tmp_path / "genome.fa"
+    data.tofile(p)
+    want = harness.oracle_count_fasta(data, 8)
+    assert_counts_equal(counter.count_file(str(p), 8), want)
+    # three file shards with look-back context, accumulated into one set of device buffers
+    acc = counter.new_accumulators(8)
+    n = len(data)
+    cuts = [0, n // 3 + 17, 2 * n // 3 + 5, n]
+    total = 0
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        lb = max(0, a - 70000)
+        sb, stop, eih = counter.count_fasta_range(data[lb:b], a - lb, 8, acc)
+        assert stop is None and not eih
+        total += sb
+    assert_counts_equal(counter.finalize_device(acc, total), want)
+
+
+# ---- full-size properties (config 4 shape; the oracle cannot run at this size in seconds) -------------
+def test_full_size_properties(counter):
+    """size-independent checks at 3.1 Gbp, k = 11: conservation (sum of counts == number of windows implied by the
+    record layout), exact additivity over a split, and agreement of two different launch decompositions"""
+    import torch
+    from findkmer_b200 import synth
+    n_bases = int(os.environ.get("FKB_TEST_FULL_BASES", 3_100_000_000))
+    lay = synth.config4(n_bases=n_bases).stripped()
+    k = 11
+    d = counter.synth_fasta_device(lay)
+    n = d.numel()
+    acc = counter.new_accumulators(k)
+    counter.count_stream_device(d, k, acc)
+    whole = counter.finalize_device(acc, n)
+    expect_windows = sum(max(0, lay.record_bases(r) - k + 1) for r in range(lay.n_records))
+    assert whole.n_kmers == expect_windows == int(whole.table.sum(dtype=np.uint64))
+    assert whole.base_total == n_bases == sum(whole.base_count) and whole.valid_bases == n_bases
+    assert whole.node_count == sum(4 ** i for i in range(k + 1))  # every 11-mer occurs ~739 times
+    acc2 = counter.new_accumulators(k)
+    cut = n // 3 + 1
+    counter.count_stream_device(d, k, acc2, 0, cut)
+    counter.count_stream_device(d, k, acc2, cut, n)
+    split = counter.finalize_device(acc2, n)
+    assert np.array_equal(split.table, whole.table)
+    assert (split.n_kmers, split.base_count, split.node_count) == (whole.n_kmers, whole.base_count, whole.node_count)
+    del d
+    torch.cuda.empty_cache()

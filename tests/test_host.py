@@ -1,0 +1,179 @@
+"""Host-side logic and the C-ABI surface, on CPU (no compute calls that need a GPU)."""
+import ctypes
+import hashlib
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_DIR, ROOT, random_fasta
+
+
+def test_library_exports_every_declared_symbol(fkb_lib):
+    from findkmer_b200 import _lib
+    header = (ROOT / "include" / "findkmer_b200.h").read_text()
+    declared = sorted(set(re.findall(r"\b(fkb_[a-z0-9_]+)\s*\(", header)))
+    assert declared, "no declarations found"
+    assert sorted(_lib.EXPORTS) == declared, "findkmer_b200/_lib.py::EXPORTS is out of sync with the header"
+    for name in declared:
+        assert getattr(fkb_lib, name) is not None, name
+
+
+def test_abi_struct_sizes_match_header(fkb_lib):
+    from findkmer_b200._lib import FkbCounts, FkbPartials
+    assert ctypes.sizeof(FkbCounts) == 12 * 8 and ctypes.sizeof(FkbPartials) == 12 * 8
+    assert fkb_lib.fkb_table_entries(11) == 4 ** 11 and fkb_lib.fkb_table_entries(17) == 0
+    assert fkb_lib.fkb_prefix_flags_bytes(11) == sum(4 ** d for d in range(1, 11))
+    assert fkb_lib.fkb_max_nodes(11) == 5592405 and fkb_lib.fkb_max_nodes(6) == 5461
+
+
+def test_no_gpu_means_loud_failure_not_fallback(fkb_lib):
+    """without a usable sm_100 device every context creation fails; there is no CPU path behind the ABI"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from findkmer_b200 import FindKmerError, _lib
+    from findkmer_b200.engine import KmerCounter
+    with pytest.raises(FindKmerError) as e:
+        KmerCounter(0)
+    assert e.value.status == _lib.FKB_ERR_CUDA
+
+
+def test_product_does_not_touch_the_oracle():
+    """the oracle is test infrastructure: nothing under findkmer_b200/ may import, link or name it"""
+    for path in (ROOT / "findkmer_b200").rglob("*"):
+        if path.suffix in {".py", ".cu", ".cuh", ".cpp", ".h"}:
+            text = path.read_text(errors="replace")
+            assert "oracle" not in text.lower(), path
+
+
+# ---- the host loader: stream contract ------------------------------------------------------------------
+def test_strip_matches_contract_on_golden_inputs(harness, golden, test_txt):
+    from findkmer_b200 import FindKmerError, _lib
+    from findkmer_b200.engine import KmerCounter
+    inputs = [test_txt] + [r["input_latin1"].encode("latin1") for r in golden["micro"]] + [random_fasta(s, 9000) for s in range(4)]
+    for data in inputs:
+        rc, want = harness.oracle_strip(data)
+        if rc == harness.FKO_OK:
+            assert bytes(KmerCounter.strip(data)) == bytes(want)
+        else:
+            with pytest.raises(FindKmerError) as e:
+                KmerCounter.strip(data)
+            assert e.value.status == {harness.FKO_ERR_EMPTY: _lib.FKB_ERR_EMPTY_INPUT,
+                                      harness.FKO_ERR_UNTERMINATED_HDR: _lib.FKB_ERR_UNTERMINATED_HEADER}[rc]
+
+
+@pytest.mark.parametrize("threads", [1, 3, 8])
+def test_strip_block_boundaries(harness, threads):
+    """> 4 MiB inputs cross loader blocks: headers, newlines and 0xFF placed on and around the block edges"""
+    from findkmer_b200 import synth
+    from findkmer_b200.engine import KmerCounter
+    data = synth.render(synth.config2(n_bases=9_500_000)).copy()
+    block = 4 << 20
+    for edge in (block, 2 * block):
+        patch = np.frombuffer(b"ACGT>this header line straddles the loader block edge ACGT>>\nACGTNNacgt\n\n\nACGT", dtype=np.uint8)
+        data[edge - 40:edge - 40 + len(patch)] = patch
+    rc, want = harness.oracle_strip(data)
+    assert rc == 0
+    assert np.array_equal(KmerCounter.strip(data, threads), want)
+    data[block + 5] = 0xFF  # inside the header that straddles the edge: skipped like any header byte
+    rc, want = harness.oracle_strip(data)
+    assert np.array_equal(KmerCounter.strip(data, threads), want)
+    data[2 * block + 35] = 0xFF  # outside a header: ends the scan
+    rc, want = harness.oracle_strip(data)
+    got = KmerCounter.strip(data, threads)
+    assert np.array_equal(got, want) and len(got) < 9_000_000
+
+
+def test_strip_giant_lines_and_header_only(harness):
+    from findkmer_b200.engine import KmerCounter
+    one_line = b">h\n" + b"ACGT" * 3_000_000 + b"\n"
+    assert np.array_equal(KmerCounter.strip(one_line, 4), harness.oracle_strip(one_line)[1])
+    giant_header = b"ACGT\n>" + b"x" * 9_000_000 + b"\nACGT\n"
+    assert bytes(KmerCounter.strip(giant_header, 4)) == b"ACGT>ACGT"
+
+
+# ---- the writer against the reference's files ---------------------------------------------------------
+def _counts_from_oracle(o, k):
+    from findkmer_b200._lib import FkbCounts
+    from findkmer_b200.engine import KmerCounts
+    c = FkbCounts()
+    c.n_kmers, c.base_total, c.node_count = o.n_kmers, o.base_total, o.node_count
+    for i in range(4):
+        c.base_count[i] = o.base_count[i]
+    return KmerCounts.from_struct(k, o.table, c)
+
+
+def test_writer_reproduces_golden_files(harness, golden, test_txt, tmp_path):
+    """product writer fed the table the reference would have built => the reference's bytes"""
+    from findkmer_b200.engine import write_outputs
+    for k, z, name in [(6, None, "6mer_Historam_Of_test.txt.csv"), (11, None, "11mer_Historam_Of_test.txt.csv"),
+                       (6, 1, "6mer_Historam_Of_test.txtzScoreFiltered_z1.csv"), (6, 2, "6mer_Historam_Of_test.txtzScoreFiltered_z2.csv")]:
+        kc = _counts_from_oracle(harness.oracle_count_fasta(test_txt, k), k)
+        csv, stats = tmp_path / "a.csv", tmp_path / "a.txt"
+        assert write_outputs(kc, csv, stats, z_threshold=z, n_threads=3) == 0
+        assert csv.read_bytes() == (GOLDEN_DIR / name).read_bytes()
+        assert stats.read_bytes() == (GOLDEN_DIR / f"{k}mer_Base_Stats_Of_test.txt.txt").read_bytes()
+    for k in (1, 3, 7, 8, 9, 10):
+        kc = _counts_from_oracle(harness.oracle_count_fasta(test_txt, k), k)
+        csv, stats = tmp_path / "b.csv", tmp_path / "b.txt"
+        write_outputs(kc, csv, stats)
+        assert hashlib.sha256(csv.read_bytes()).hexdigest() == golden["test_txt"][str(k)]["csv_sha256"]
+        assert hashlib.sha256(stats.read_bytes()).hexdigest() == golden["test_txt"][str(k)]["stats_sha256"]
+
+
+def test_writer_edge_cases_against_golden(harness, golden, tmp_path):
+    """zero-probability base => header-only CSV + status; no run >= k => NaN statistics, no rows"""
+    from findkmer_b200 import _lib
+    from findkmer_b200.engine import write_outputs
+    for rec in golden["micro"]:
+        data = rec["input_latin1"].encode("latin1")
+        if rec["hung"] or data == b"":
+            continue
+        k = rec["k"]
+        kc = _counts_from_oracle(harness.oracle_count_fasta(data, k), k)
+        csv, stats = tmp_path / "c.csv", tmp_path / "c.txt"
+        status = write_outputs(kc, csv, stats)
+        assert (status == _lib.FKB_ERR_ZERO_BASE_PROBABILITY) == rec["division_overflow"], rec
+        assert hashlib.sha256(csv.read_bytes()).hexdigest() == rec["csv_sha256"], rec
+        assert hashlib.sha256(stats.read_bytes()).hexdigest() == rec["stats_sha256"], rec
+
+
+def test_writer_live_against_reference_binary(harness, tmp_path):
+    if not harness.reference_available():
+        pytest.skip("reference binary not built")
+    from findkmer_b200 import synth
+    from findkmer_b200.engine import write_outputs
+    data = synth.render(synth.config2(n_bases=400_000))
+    for k, z in ((7, None), (9, 3), (11, None)):
+        r = harness.run_reference(data, k, z=z)
+        kc = _counts_from_oracle(harness.oracle_count_fasta(data, k), k)
+        csv, stats = tmp_path / "d.csv", tmp_path / "d.txt"
+        assert write_outputs(kc, csv, stats, z_threshold=z) == 0
+        assert csv.read_bytes() == r.csv and stats.read_bytes() == r.stats
+
+
+# ---- synthetic inputs -----------------------------------------------------------------------------------
+def test_synth_layouts_are_deterministic_and_shaped():
+    from findkmer_b200 import synth
+    lay = synth.config3(n_records=5)
+    f = bytes(synth.render(lay))
+    lines = f.split(b"\n")
+    assert lines[0] == b">ENST00000000000" and len(lines[1]) == 1001 and set(lines[1]) <= set(b"ACGT")
+    assert hashlib.sha256(f).hexdigest() == hashlib.sha256(bytes(synth.render(synth.config3(n_records=5)))).hexdigest()
+    lay2 = synth.config2(n_bases=1000)
+    f2 = bytes(synth.render(lay2))
+    assert all(len(ln) <= 60 for ln in f2.split(b"\n")) and f2.count(b">") == 16 and len(f2) == lay2.total_bytes
+    f5 = synth.render(synth.config5(n_bases=2_000_000))
+    frac_n = np.count_nonzero(f5 == ord("N")) / 2e6
+    frac_lc = np.count_nonzero((f5 >= ord("a")) & (f5 <= ord("z")) & (np.cumsum(f5 == 10) >= 0)) / 2e6
+    assert 0.02 < frac_n < 0.09 and 0.05 < frac_lc < 0.2
+    assert synth.config4().record_bases(0) < 2 ** 31  # the reference's seqSize is an int
+
+
+def test_stripped_layout_equals_loader_output():
+    from findkmer_b200 import synth
+    from findkmer_b200.engine import KmerCounter
+    for lay in (synth.config2(n_bases=100_001), synth.config3(n_records=40), synth.config5(n_bases=120_000)):
+        assert np.array_equal(KmerCounter.strip(synth.render(lay)), synth.stripped_stream(lay))
