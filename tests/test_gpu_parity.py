@@ -223,7 +223,7 @@ def test_count_file_and_range_shards(counter, harness, tmp_path):
     for a, b in zip(cuts[:-1], cuts[1:]):
         lb = max(0, a - 70000)
         sb, stop, eih = counter.count_fasta_range(data[lb:b], a - lb, 8, acc)
-        assert stop is None and not eih
+        assert stop is None and (not eih or b < n)  # a cut may fall inside a header line; only the file's end must not
         total += sb
     assert_counts_equal(counter.finalize_device(acc, total), want)
 
