@@ -49,6 +49,8 @@ struct fkb_context {
     fkb_partials *d_partials = nullptr;
     int table_k = 0;
 
+    fkb::BucketScratch bucket;  // scratch of the bucketed count path (grown on demand)
+
     // pinned staging ring for the loader
     static constexpr int kSlots = 12;
     size_t slot_bytes = 0;
@@ -80,7 +82,34 @@ int fail(fkb_context *ctx, int status, const char *fmt, ...)
             return fail((ctx), FKB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
 
-fkb::LaunchInfo launch_info(const fkb_context *ctx) { return fkb::LaunchInfo{ctx->sm_count, ctx->forced_variant}; }
+fkb::LaunchInfo launch_info(const fkb_context *ctx) { return fkb::LaunchInfo{ctx->sm_count, ctx->forced_variant, ctx->bucket}; }
+
+// Scratch of the bucketed path, sized for a range of `range_bytes` at word stride S: one private segment per
+// (bucket, pass-1 CTA) of 4x the average fill (real genomes are skewed; anything beyond escapes exactly through
+// global reds), the segment fills and the 16-bit W-mer table.  HBM is plentiful: 3.1 Gbp at k = 11 takes ~8.4 GB.
+int ensure_bucket_scratch(fkb_context *ctx, int k, uint64_t range_bytes)
+{
+    const int S = fkb::bucket_stride_for(k);
+    if (!S || ctx->forced_variant == fkb::VARIANT_DIRECT) return FKB_OK;
+    if (range_bytes < (64ull << 20) && ctx->forced_variant != fkb::VARIANT_BUCKET) return FKB_OK;  // the direct kernel will run
+    const uint64_t items = range_bytes / S + 1;
+    const uint64_t nb = (uint64_t)fkb::bucket_count(), n_cta = (uint64_t)ctx->sm_count;
+    uint64_t cap = (4 * (items / (nb * n_cta)) + 64 + 7) & ~7ull;
+    if (cap > 0x7FFFFFF8ull) cap = 0x7FFFFFF8ull;
+    if (ctx->bucket.gbuf && ctx->bucket.cap_cb >= cap) return FKB_OK;
+    if (ctx->bucket.gbuf) cudaFree(ctx->bucket.gbuf);
+    ctx->bucket.gbuf = nullptr;
+    ctx->bucket.cap_cb = 0;
+    ctx->bucket.n_cta = (int)n_cta;
+    if (!ctx->bucket.gcount) {
+        FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.gcount, nb * n_cta * sizeof(uint32_t)));
+        FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.work, 64));
+    }
+    if (!ctx->bucket.table_w) FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.table_w, fkb::bucket_table_w_bytes()));
+    FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.gbuf, nb * n_cta * cap * sizeof(uint16_t)));
+    ctx->bucket.cap_cb = (uint32_t)cap;
+    return FKB_OK;
+}
 
 int check_k(fkb_context *ctx, int k)
 {
@@ -375,6 +404,10 @@ void fkb_destroy(fkb_context *ctx)
         if (ctx->slots[i]) cudaFreeHost(ctx->slots[i]);
         if (ctx->slot_free[i]) cudaEventDestroy(ctx->slot_free[i]);
     }
+    if (ctx->bucket.gbuf) cudaFree(ctx->bucket.gbuf);
+    if (ctx->bucket.gcount) cudaFree(ctx->bucket.gcount);
+    if (ctx->bucket.work) cudaFree(ctx->bucket.work);
+    if (ctx->bucket.table_w) cudaFree(ctx->bucket.table_w);
     if (ctx->d_stream) cudaFree(ctx->d_stream);
     if (ctx->d_table) cudaFree(ctx->d_table);
     if (ctx->d_flags) cudaFree(ctx->d_flags);
@@ -399,6 +432,16 @@ int fkb_device_info(fkb_context *ctx, int *sm_count, int *cc_major, int *cc_mino
     if (cc_minor) *cc_minor = ctx->cc_minor;
     if (hbm_bytes) *hbm_bytes = ctx->hbm_bytes;
     return FKB_OK;
+}
+
+int fkb_set_option(fkb_context *ctx, const char *name, long value)
+{
+    if (!ctx || !name) return FKB_ERR_BAD_ARG;
+    if (!strcmp(name, "variant") && value >= 0 && value <= 2) {
+        ctx->forced_variant = (int)value;
+        return FKB_OK;
+    }
+    return fail(ctx, FKB_ERR_BAD_ARG, "unknown option %s=%ld", name, value);
 }
 
 int fkb_alloc_pinned(fkb_context *ctx, size_t bytes, void **ptr)
@@ -491,6 +534,7 @@ int fkb_count_stream_device(fkb_context *ctx, const uint8_t *d_stream, uint64_t 
     if (end < begin) return fail(ctx, FKB_ERR_BAD_ARG, "end < begin");
     if (end == begin) return FKB_OK;
     if (!d_stream || ((uintptr_t)d_stream & 15)) return fail(ctx, FKB_ERR_BAD_ARG, "d_stream must be a 16-byte aligned device pointer");
+    if (int s = ensure_bucket_scratch(ctx, k, end - begin)) return s;
     int launches = 0;
     FKB_CUDA(ctx, fkb::launch_count(launch_info(ctx), d_stream, begin, end, k, d_table, d_flags, d_partials, (cudaStream_t)cuda_stream, &launches));
     ctx->launches += launches;

@@ -1,0 +1,524 @@
+// fkb_bucket.cu -- VARIANT_BUCKET: the count path for large inputs, built around what profiles/
+// r01_ubench_atomics measured on B200: random global `red`s stop at ~190 Gop/s, shared-memory atomics run at
+// ~2600 Gop/s.  So the k-mers are ROUTED to a CTA that owns their bins in shared memory, and the number of
+// routed items is cut by counting longer words:
+//
+//   Instead of one update per k-mer, count W-mers (W = 13 >= k) at every S-th stream position (S = W - k + 1,
+//   positions p == 0 mod S).  A fully valid W-window at p contains the S k-mers that start at p .. p+S-1, so the
+//   k-mer table is recovered EXACTLY by a fold:  T_k[x] = sum over offsets t < S and all (t-base prefixes a,
+//   (S-1-t)-base suffixes b) of T_W[a x b],  plus the few "leftover" k-mers whose covering W-window is broken
+//   by a reset or a range edge (those go straight to T_k with a global red).  At k = 11 that is 3x fewer items.
+//
+//   pass 1  bucketize : every warp streams a contiguous region of the stream, software-pipelined one iteration
+//                       ahead (128-bit loads).  Fused ASCII->2-bit encode + validity (SIMD in 32-bit registers,
+//                       16 bases per word) + window extraction; item = 26-bit W-mer code, bucket = top 10 bits
+//                       (1024 buckets), payload = low 16 bits.  Items are staged per bucket in shared memory (the
+//                       shared atomicAdd returns the slot) and appended, in 16-byte chunks, to a region of HBM that
+//                       is private to (bucket, CTA) -- no global atomics on the routing path.
+//   pass 2  count     : one CTA at a time owns a bucket's 65536 16-bit counters (128 KiB of shared memory), streams
+//                       the bucket's payloads with 128-bit loads and counts with shared-memory atomics; a counter
+//                       that reaches 0x8000 drains exactly to T_k.  The sub-table is written out once.
+//   pass 3  fold      : T_k[x] += gathered sums of T_W (coalesced reads, no atomics).
+//
+// Semantics are those of the reference's scan (findKmer/src/findKmer.cpp:962-1069) exactly; the rare per-run
+// events (seqSize == k, :1044-1057; seqSize < k, :1059-1062) are derived from the validity bit masks.
+// profiles/r01_ncu_bucketize_v1_by_line.txt is the instruction profile of the first version of pass 1 that this
+// layout answers (38 % of instructions in the flush copy loop, 15 % in run-mask loops, a barrier per iteration).
+#include "fkb_kernels.cuh"
+
+namespace fkb {
+
+namespace {
+
+constexpr int kW = 13;                       // counted word length
+constexpr int kBucketBits = 2 * kW - 16;     // 10
+constexpr int kNB = 1 << kBucketBits;        // 1024 buckets
+constexpr int kP1Threads = 512;
+constexpr int kP1Warps = kP1Threads / 32;
+constexpr int kStageCap = 96;                // staged items per bucket (12 chunks of 8)
+constexpr int kTileIters = 5;                // warp iterations between flushes: 5 * 8192 items / 1024 buckets = 40 avg (+ <= 7 carried)
+constexpr int kP2Threads = 1024;
+
+__host__ __device__ inline uint64_t flags_offset(int d) { return ((1ull << (2 * d)) - 4ull) / 3ull; }
+
+__device__ __forceinline__ uint4 ldg128(const uint8_t *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void red_add_u32(uint32_t *addr, uint32_t v)
+{
+    asm volatile("red.global.add.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- SIMD-in-register encode of 4 ASCII bytes (one 32-bit word, byte 0 = lowest address) ----------------
+// codes: 8 bits, byte 0's 2-bit code in bits 7..6 (A0 C1 G2 T3 = base2int, findKmer.cpp:569-576)
+// bad  : a word whose byte i is ZERO iff input byte i is one of A,C,G,T.
+//   A 0x41, C 0x43, G 0x47, T 0x54: bits 7,6,5,3 must read 0,1,0,0; with q = b2 & ~b1 the rest must satisfy
+//   b4 == q and b0 == ~q (A,C,G: q = 0 for A and C, 1 for G ... T: b2 = 1, b1 = 0 -> q = 1, b4 = 1, b0 = 0; G: b2 = b1 = 1 -> q = 0).
+__device__ __forceinline__ void encode_word(uint32_t w, uint32_t &codes, uint32_t &bad)
+{
+    const uint32_t p1 = w >> 1, p2 = w >> 2, p4 = w >> 4;
+    const uint32_t t = (p1 ^ p2) & 0x03030303u;
+    codes = (t * 0x40100401u) >> 24;
+    const uint32_t q = p2 & ~p1;
+    const uint32_t lo_bad = ((p4 ^ q) | ~(w ^ q)) & 0x01010101u;
+    bad = ((w & 0xE8E8E8E8u) ^ 0x40404040u) | lo_bad;
+}
+// 4-bit mask (byte 0 -> bit 3) of the ZERO bytes of u
+__device__ __forceinline__ uint32_t zero_bytes_nibble(uint32_t u)
+{
+    uint32_t nz = (((u & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | u) & 0x80808080u;  // bit 7 of every non-zero byte
+    uint32_t f = (nz ^ 0x80808080u) >> 7;                                  // bit 0 of every zero byte
+    return (f * 0x08040201u) >> 24;                                        // byte0->bit3 ... byte3->bit0
+}
+__device__ __forceinline__ uint32_t count_bytes_equal(uint32_t w, uint32_t splat) { return __popc(zero_bytes_nibble(w ^ splat)); }
+
+struct Group {
+    uint32_t code;   // 16 bases x 2 bits, first byte in bits 31..30
+    uint32_t valid;  // 16 bits, first byte in bit 15
+};
+
+// pack 16 bytes; `unknown` accumulates the bytes outside {A,C,G,T,N,'>'} (one stderr line each in the reference, :581-585)
+__device__ __forceinline__ Group pack_group(const uint4 &g, uint32_t &unknown)
+{
+    Group r;
+    uint32_t c0, c1, c2, c3, b0, b1, b2, b3;
+    encode_word(g.x, c0, b0);
+    encode_word(g.y, c1, b1);
+    encode_word(g.z, c2, b2);
+    encode_word(g.w, c3, b3);
+    r.code = (c0 << 24) | (c1 << 16) | (c2 << 8) | c3;
+    r.valid = 0xFFFFu;
+    if ((b0 | b1 | b2 | b3) != 0) {  // rare in sequence data: some byte is not a base
+        r.valid = (zero_bytes_nibble(b0) << 12) | (zero_bytes_nibble(b1) << 8) | (zero_bytes_nibble(b2) << 4) | zero_bytes_nibble(b3);
+        uint32_t nN = count_bytes_equal(g.x, 0x4E4E4E4Eu) + count_bytes_equal(g.y, 0x4E4E4E4Eu) + count_bytes_equal(g.z, 0x4E4E4E4Eu) +
+                      count_bytes_equal(g.w, 0x4E4E4E4Eu);
+        uint32_t nH = count_bytes_equal(g.x, 0x3E3E3E3Eu) + count_bytes_equal(g.y, 0x3E3E3E3Eu) + count_bytes_equal(g.z, 0x3E3E3E3Eu) +
+                      count_bytes_equal(g.w, 0x3E3E3E3Eu);
+        unknown += 16 - __popc(r.valid) - nN - nH;
+    }
+    return r;
+}
+
+// bits b of m (earlier bytes in higher bits) such that bits b .. b+LEN-1 are all set, by doubling
+template <int LEN>
+__device__ __forceinline__ uint32_t runs_of(uint32_t m)
+{
+    if constexpr (LEN == 1) {
+        return m;
+    } else {
+        constexpr int H = LEN / 2;
+        const uint32_t h = runs_of<H>(m);
+        uint32_t r = h & (h >> H);
+        if constexpr (LEN & 1) r &= (m >> (LEN - 1));
+        return r;
+    }
+}
+
+// S k-mers of one W-mer: every exact escape (staging overflow, region overflow, counter drain) goes through here
+template <int S>
+__device__ __noinline__ void red_kmers_of_word(uint32_t wcode, uint32_t *table_k, uint32_t amount)
+{
+    constexpr int K = kW - S + 1;
+    constexpr uint32_t kmask = (1u << (2 * K)) - 1u;
+#pragma unroll
+    for (int t = 0; t < S; ++t) red_add_u32(table_k + ((wcode >> (2 * (S - 1 - t))) & kmask), amount);
+}
+
+// rare per-run events of one group (positions given as bits of 16-bit masks, first byte = bit 15)
+__device__ __noinline__ void group_events(uint32_t first_k, uint32_t shorts, uint32_t m32, uint32_t code_hi, uint32_t code_lo, int k,
+                                          uint8_t *flags, fkb_partials *P)
+{
+    const uint32_t kmask = (k == 16) ? 0xffffffffu : ((1u << (2 * k)) - 1u);
+    while (first_k) {  // run length reached exactly k here: first k-1 bases of the window go to head_base (:1050-1056)
+        int b = 31 - __clz(first_k);
+        first_k &= ~(1u << b);
+        uint32_t kmer = __funnelshift_r(code_lo, code_hi, 2 * b) & kmask;
+        uint32_t head = kmer >> 2, cnt[4] = {0, 0, 0, 0};
+        for (int i = 0; i < k - 1; ++i) { cnt[head & 3u]++; head >>= 2; }
+        for (int c = 0; c < 4; ++c)
+            if (cnt[c]) atomicAdd(&P->head_base[c], (unsigned long long)cnt[c]);
+        atomicAdd(&P->runs_ge_k, 1ull);
+    }
+    while (shorts) {  // valid base whose run is still shorter than k: the reference inserts a short path (:1059-1062)
+        int b = 31 - __clz(shorts);
+        shorts &= ~(1u << b);
+        int run = __ffs(~(m32 >> b)) - 1;  // consecutive valid bytes ending here (1 .. k-1)
+        uint32_t prefix = __funnelshift_r(code_lo, code_hi, 2 * b) & ((1u << (2 * run)) - 1u);
+        flags[flags_offset(run) + prefix] = 1;
+        atomicAdd(&P->short_first[prefix >> (2 * (run - 1))], 1ull);
+    }
+}
+
+__device__ __noinline__ void leftover_kmers(uint32_t left, uint32_t code_hi, uint32_t code_lo, uint32_t kmask, uint32_t *table_k)
+{
+    while (left) {  // k-mers whose covering W-window is broken (run edges / range edges): straight to T_k
+        int b = 31 - __clz(left);
+        left &= ~(1u << b);
+        red_add_u32(table_k + (__funnelshift_r(code_lo, code_hi, 2 * b) & kmask), 1u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 1: bucketize.  The interior starts at `lo` (a multiple of 16*S in absolute stream coordinates) and is
+// n_witers warp-iterations of 32 * 16*S bytes long; 16 readable bytes exist on both sides of it.
+// ------------------------------------------------------------------------------------------------
+struct P1Smem {
+    uint16_t stage[kNB * kStageCap];
+    uint32_t cursor[kNB];  // items staged in the row
+    uint32_t goff[kNB];    // items already appended to this CTA's region of the bucket (multiple of 8 until the end)
+};
+
+template <int S>
+__global__ void __launch_bounds__(kP1Threads, 1)
+bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, uint16_t *__restrict__ gbuf, uint32_t cap_cb,
+                 uint32_t *__restrict__ gcount, uint32_t *__restrict__ table_k, uint8_t *__restrict__ flags, fkb_partials *__restrict__ P)
+{
+    static_assert(S >= 1 && S <= 8, "stride");
+    constexpr int K = kW - S + 1;
+    constexpr int CH = 16 * S;                     // bytes per lane per iteration: exactly 16 items
+    constexpr int J = S - 1;
+    constexpr uint32_t WMASK = (1u << (2 * kW)) - 1u;
+    constexpr uint32_t KMASK = (1u << (2 * K)) - 1u;
+    constexpr uint64_t WSPAN = 32ull * CH;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    P1Smem &sm = *reinterpret_cast<P1Smem *>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    for (int b = threadIdx.x; b < kNB; b += kP1Threads) { sm.cursor[b] = 0; sm.goff[b] = 0; }
+    __syncthreads();
+
+    // this warp's contiguous share of the interior
+    const uint64_t n_warps = (uint64_t)gridDim.x * kP1Warps, gw = (uint64_t)blockIdx.x * kP1Warps + warp;
+    const uint64_t q = n_witers / n_warps, rem = n_witers % n_warps;
+    const uint64_t my_iters = q + (gw < rem ? 1 : 0);
+    const uint64_t my_first = gw * q + (gw < rem ? gw : rem);
+    const uint64_t max_iters = q + (rem ? 1 : 0);          // CTA-uniform trip count (barriers)
+    const uint64_t region = lo + my_first * WSPAN, hi = lo + n_witers * WSPAN;
+    uint16_t *const my_gbuf = gbuf + (uint64_t)blockIdx.x * cap_cb;  // + bucket * gridDim.x * cap_cb
+
+    uint32_t t_unknown = 0, t_dummy = 0;
+    unsigned long long t_windows = 0, t_valid = 0;
+
+    // ---- software pipeline: `cur` = packed groups of iteration it, `nxt` = of it+1, `raw` = loads of it+2 in flight ----
+    Group cur[S], nxt[S], carry;   // carry: the 16 bytes in front of lane 0's chunk (previous iteration's lane 31, last group)
+    uint4 raw[S];
+    auto issue_loads = [&](uint64_t it) {  // iteration index it may be my_iters (only lane 0's first group: the right halo) or beyond (nothing)
+        const uint64_t base = region + it * WSPAN + (uint64_t)lane * CH;
+#pragma unroll
+        for (int g = 0; g < S; ++g) {
+            const bool need = it < my_iters || (it == my_iters && lane == 0 && g == 0);
+            raw[g] = need ? ldg128(s + base + 16 * g) : make_uint4(0, 0, 0, 0);
+        }
+    };
+    {
+        carry = pack_group(ldg128(s + region - 16), t_dummy);  // left halo of the region (same address for all lanes)
+        issue_loads(0);
+#pragma unroll
+        for (int g = 0; g < S; ++g) cur[g] = pack_group(raw[g], my_iters > 0 ? t_unknown : t_dummy);
+        issue_loads(1);
+#pragma unroll
+        for (int g = 0; g < S; ++g) nxt[g] = pack_group(raw[g], my_iters > 1 ? t_unknown : t_dummy);
+        issue_loads(2);
+    }
+
+    for (uint64_t tile0 = 0; tile0 < max_iters; tile0 += kTileIters) {
+        for (uint64_t it = tile0; it < tile0 + kTileIters && it < my_iters; ++it) {
+            // ---- neighbours: grp[0] = 16 bytes before my chunk, grp[1..S] = my chunk, grp[S+1] = 16 bytes after it ----
+            Group grp[S + 2];
+#pragma unroll
+            for (int g = 0; g < S; ++g) grp[g + 1] = cur[g];
+            grp[0].code = __shfl_up_sync(0xffffffffu, cur[S - 1].code, 1);
+            grp[0].valid = __shfl_up_sync(0xffffffffu, cur[S - 1].valid, 1);
+            grp[S + 1].code = __shfl_down_sync(0xffffffffu, cur[0].code, 1);
+            grp[S + 1].valid = __shfl_down_sync(0xffffffffu, cur[0].valid, 1);
+            const uint32_t n0c = __shfl_sync(0xffffffffu, nxt[0].code, 0), n0v = __shfl_sync(0xffffffffu, nxt[0].valid, 0);
+            const uint32_t l31c = __shfl_sync(0xffffffffu, cur[S - 1].code, 31), l31v = __shfl_sync(0xffffffffu, cur[S - 1].valid, 31);
+            if (lane == 0) grp[0] = carry;
+            if (lane == 31) { grp[S + 1].code = n0c; grp[S + 1].valid = n0v; }
+            carry.code = l31c;
+            carry.valid = l31v;
+
+            const uint64_t cbase = region + it * WSPAN + (uint64_t)lane * CH;
+            uint32_t vall = grp[0].valid & grp[S + 1].valid;
+#pragma unroll
+            for (int g = 1; g <= S; ++g) vall &= grp[g].valid;
+            const bool edge = (cbase == lo) || (cbase + CH == hi);
+
+            uint32_t emit[S + 2];
+            if (vall == 0xFFFFu && !edge) {
+                // ---- fast path: 16*(S+2) valid bases around me: every anchored window exists, nothing is left over ----
+#pragma unroll
+                for (int g = 1; g <= S; ++g) {
+                    uint32_t phase = 0;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if ((16 * (g - 1) + i) % S == (kW - 1) % S) phase |= 1u << (15 - i);
+                    emit[g] = phase;
+                }
+                t_windows += 16 * S;
+                t_valid += 16 * S;
+            } else {
+                // ---- general path: window masks per group; emit = fully valid W-window ending at an anchored position ----
+#pragma unroll
+                for (int g = 1; g <= S + 1; ++g) {
+                    const uint32_t m = (grp[g - 1].valid << 16) | grp[g].valid;
+                    uint32_t phase = 0;  // anchored ends: (16*(g-1) + i) == W-1 (mod S), i = byte in group, bit = 15 - i
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if ((16 * (g - 1) + i) % S == (kW - 1) % S) phase |= 1u << (15 - i);
+                    emit[g] = runs_of<kW>(m) & phase;
+                }
+                if (cbase + CH == hi) emit[S + 1] = 0;        // windows ending beyond hi belong to nobody here: their k-mers are leftovers
+                if (cbase == lo) emit[1] &= (0xFFFFu >> J);   // a window whose first covered k-mer ends before lo is not ours
+#pragma unroll
+                for (int g = 1; g <= S; ++g) {
+                    const uint32_t m = (grp[g - 1].valid << 16) | grp[g].valid;
+                    const uint32_t rk = runs_of<K>(m) & 0xFFFFu;
+                    t_windows += __popc(rk);
+                    t_valid += __popc(grp[g].valid);
+                    const uint32_t E = (emit[g] << 16) | emit[g + 1];  // k-mers covered by an emitted window: it ends 0..J bytes later
+                    uint32_t cov = E;
+#pragma unroll
+                    for (int d = 1; d <= J; ++d) cov |= (E << d);
+                    const uint32_t left = rk & ~(cov >> 16);
+                    if (left) leftover_kmers(left, grp[g - 1].code, grp[g].code, KMASK, table_k);
+                    if (m != 0xFFFFFFFFu) {
+                        const uint32_t first_k = rk & ~(m >> K) & 0xFFFFu;
+                        const uint32_t shorts = grp[g].valid & ~rk;
+                        if (first_k | shorts) group_events(first_k, shorts, m, grp[g - 1].code, grp[g].code, K, flags, P);
+                    }
+                }
+            }
+
+            // ---- the 16 items of this chunk: static slots ----
+#pragma unroll
+            for (int g = 1; g <= S; ++g) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    if ((16 * (g - 1) + i) % S != (kW - 1) % S) continue;
+                    if (emit[g] & (1u << (15 - i))) {
+                        const uint32_t wcode = __funnelshift_r(grp[g].code, grp[g - 1].code, 2 * (15 - i)) & WMASK;
+                        const uint32_t bucket = wcode >> 16;
+                        const uint32_t pos = atomicAdd(&sm.cursor[bucket], 1u);
+                        if (pos < (uint32_t)kStageCap) sm.stage[bucket * kStageCap + pos] = (uint16_t)wcode;
+                        else red_kmers_of_word<S>(wcode, table_k, 1u);  // staging row full (skewed input): exact escape
+                    }
+                }
+            }
+
+            // ---- advance the pipeline ----
+#pragma unroll
+            for (int g = 0; g < S; ++g) cur[g] = nxt[g];
+#pragma unroll
+            for (int g = 0; g < S; ++g) nxt[g] = pack_group(raw[g], (it + 2 < my_iters) ? t_unknown : t_dummy);
+            issue_loads(it + 3);
+        }
+
+        // ---- flush: append whole 16-byte chunks of every staged row to this CTA's region of the bucket ----
+        __syncthreads();
+        {
+            const int sub = lane >> 3, c = lane & 7;  // 4 buckets per warp step, 8 lanes each
+            for (int r = 0; r < kNB / kP1Warps / 4; ++r) {
+                const int b = warp * (kNB / kP1Warps) + r * 4 + sub;
+                const uint32_t cnt = min(sm.cursor[b], (uint32_t)kStageCap);
+                const uint32_t n8 = cnt & ~7u, off = sm.goff[b];
+                uint16_t *row = &sm.stage[b * kStageCap];
+                uint16_t *dst = my_gbuf + (uint64_t)b * gridDim.x * cap_cb + off;
+                uint4 tail = make_uint4(0, 0, 0, 0);
+                if (c == 0 && n8 && cnt > n8) tail = *reinterpret_cast<const uint4 *>(row + n8);  // the <= 7 items that stay staged
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const uint32_t i0 = (uint32_t)(c + 8 * cc) * 8u;
+                    if (i0 < n8) {
+                        const uint4 v = *reinterpret_cast<const uint4 *>(row + i0);
+                        if (off + i0 + 8 <= cap_cb) {
+                            *reinterpret_cast<uint4 *>(dst + i0) = v;
+                        } else {  // this CTA's region of the bucket is full (heavily skewed input): exact escape
+                            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+                            for (int e = 0; e < 8; ++e)
+                                red_kmers_of_word<S>(((uint32_t)b << 16) | ((w4[e >> 1] >> (16 * (e & 1))) & 0xFFFFu), table_k, 1u);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (c == 0) {
+                    if (n8 && cnt > n8) *reinterpret_cast<uint4 *>(row) = tail;
+                    sm.cursor[b] = cnt - n8;
+                    sm.goff[b] = min(off + n8, cap_cb & ~7u);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- end: the <= 7 items still staged per bucket, then this CTA's fill of every bucket ----
+    for (int b = threadIdx.x; b < kNB; b += kP1Threads) {
+        const uint32_t cnt = sm.cursor[b];
+        uint32_t off = sm.goff[b];
+        uint16_t *dst = my_gbuf + (uint64_t)b * gridDim.x * cap_cb;
+        for (uint32_t i = 0; i < cnt; ++i) {
+            const uint16_t item = sm.stage[b * kStageCap + i];
+            if (off < cap_cb) dst[off++] = item;
+            else red_kmers_of_word<S>(((uint32_t)b << 16) | item, table_k, 1u);
+        }
+        gcount[(uint64_t)b * gridDim.x + blockIdx.x] = off;
+    }
+    t_windows = warp_sum(t_windows);
+    t_valid = warp_sum(t_valid);
+    unsigned long long t_unk = warp_sum((unsigned long long)t_unknown);
+    if (lane == 0) {
+        if (t_windows) atomicAdd(&P->n_windows, t_windows);
+        if (t_valid) atomicAdd(&P->valid_bases, t_valid);
+        if (t_unk) atomicAdd(&P->unknown_chars, t_unk);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 2: per bucket, 65536 16-bit counters in shared memory; one shared atomicAdd per item.
+// The bucket's items lie in n_seg CTA-private segments; warps take whole segments.
+// ------------------------------------------------------------------------------------------------
+template <int S>
+__device__ __noinline__ void drain_counter(uint32_t *word, uint32_t hi_half, uint32_t wcode, uint32_t *table_k)
+{
+    atomicSub(word, hi_half ? 0x80000000u : 0x8000u);
+    red_kmers_of_word<S>(wcode, table_k, 32768u);
+}
+
+template <int S>
+__global__ void __launch_bounds__(kP2Threads, 1)
+count_buckets_kernel(const uint16_t *__restrict__ gbuf, uint32_t cap_cb, const uint32_t *__restrict__ gcount, int n_seg,
+                     uint16_t *__restrict__ table_w, uint32_t *__restrict__ table_k, uint32_t *__restrict__ work)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint32_t *sub = reinterpret_cast<uint32_t *>(smem_raw);  // 32768 words = 65536 packed 16-bit counters
+    __shared__ uint32_t s_bucket, s_next_seg;
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        if (threadIdx.x == 0) { s_bucket = atomicAdd(work, 1u); s_next_seg = 0; }
+        for (int i = threadIdx.x; i < 32768 / 4; i += kP2Threads) reinterpret_cast<uint4 *>(sub)[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        const uint32_t b = s_bucket;
+        if (b >= (uint32_t)kNB) break;
+        // Two 16-bit counters per word.  A counter is drained at 0x8000 (not at 0xFFFF) so that a carry can never
+        // cross into its neighbour, whatever the interleaving of the other threads' updates: the increment that
+        // sees 0x7FFF moves 32768 counts to T_k exactly and takes them out of the half again.
+        auto add_item = [&](uint32_t idx) {
+            const uint32_t hi_half = idx & 1u;
+            uint32_t *word = sub + (idx >> 1);
+            const uint32_t old = atomicAdd(word, hi_half ? 0x10000u : 1u);
+            const uint32_t half = hi_half ? (old >> 16) : (old & 0xFFFFu);
+            if (half == 0x7FFFu) drain_counter<S>(word, hi_half, (b << 16) | idx, table_k);
+        };
+        for (;;) {
+            uint32_t seg = 0;
+            if (lane == 0) seg = atomicAdd(&s_next_seg, 1u);
+            seg = __shfl_sync(0xffffffffu, seg, 0);
+            if (seg >= (uint32_t)n_seg) break;
+            const uint32_t n = min(gcount[(uint64_t)b * n_seg + seg], cap_cb);
+            const uint16_t *items = gbuf + ((uint64_t)b * n_seg + seg) * cap_cb;  // 16-byte aligned: cap_cb is a multiple of 8
+            const uint32_t n8 = n & ~7u;
+            for (uint32_t i = lane * 8u; i < n8; i += 256u) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(items + i);
+                add_item(v.x & 0xFFFFu); add_item(v.x >> 16);
+                add_item(v.y & 0xFFFFu); add_item(v.y >> 16);
+                add_item(v.z & 0xFFFFu); add_item(v.z >> 16);
+                add_item(v.w & 0xFFFFu); add_item(v.w >> 16);
+            }
+            if ((uint32_t)lane < n - n8) add_item(items[n8 + lane]);
+        }
+        __syncthreads();
+        uint4 *out = reinterpret_cast<uint4 *>(table_w + ((uint64_t)b << 16));
+        for (int i = threadIdx.x; i < 32768 / 4; i += kP2Threads) out[i] = reinterpret_cast<const uint4 *>(sub)[i];
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 3: fold T_W (16-bit) into T_k (32-bit).  Thread x gathers, for every offset t of the k-mer inside the
+// word, the 4^t prefixes a (strided) times the 4^(J-t) suffixes (contiguous).  Consecutive x are contiguous.
+// ------------------------------------------------------------------------------------------------
+template <int S>
+__global__ void __launch_bounds__(256) fold_kernel(const uint16_t *__restrict__ table_w, uint32_t *__restrict__ table_k)
+{
+    constexpr int J = S - 1, K = kW - S + 1;
+    const uint64_t n = 1ull << (2 * K);
+    for (uint64_t x = (uint64_t)blockIdx.x * 256 + threadIdx.x; x < n; x += (uint64_t)gridDim.x * 256) {
+        uint32_t sum = 0;
+#pragma unroll
+        for (int t = 0; t <= J; ++t) {
+            const int suf = J - t;                        // bases after the k-mer
+            const uint64_t mid = x << (2 * suf);
+            for (uint32_t a = 0; a < (1u << (2 * t)); ++a) {
+                const uint16_t *p = table_w + (((uint64_t)a << (2 * (kW - t))) | mid);
+                for (uint32_t b = 0; b < (1u << (2 * suf)); ++b) sum += p[b];
+            }
+        }
+        if (sum) table_k[x] += sum;
+    }
+}
+
+template <int S>
+cudaError_t run_bucketed(const LaunchInfo &li, const BucketScratch &bs, const uint8_t *d_stream, uint64_t lo, uint64_t hi,
+                         uint32_t *d_table, uint8_t *d_flags, fkb_partials *d_partials, cudaStream_t st, int *launches)
+{
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(bucketize_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P1Smem));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(count_buckets_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const uint64_t wspan = 32ull * 16 * S;
+    const uint64_t n_witers = (hi - lo) / wspan;
+    cudaError_t e = cudaMemsetAsync(bs.work, 0, 16, st);
+    if (e != cudaSuccess) return e;
+    bucketize_kernel<S><<<bs.n_cta, kP1Threads, sizeof(P1Smem), st>>>(d_stream, lo, n_witers, bs.gbuf, bs.cap_cb, bs.gcount, d_table, d_flags, d_partials);
+    count_buckets_kernel<S><<<li.sm_count, kP2Threads, 128 * 1024, st>>>(bs.gbuf, bs.cap_cb, bs.gcount, bs.n_cta, bs.table_w, d_table, bs.work);
+    constexpr int K = kW - S + 1;
+    const uint64_t n = 1ull << (2 * K);
+    uint64_t fb = (n + 255) / 256, cap = (uint64_t)li.sm_count * 8;
+    fold_kernel<S><<<(int)(fb < cap ? fb : cap), 256, 0, st>>>(bs.table_w, d_table);
+    if (launches) *launches += 3;
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+int bucket_stride_for(int k) { return (k >= 6 && k <= kW) ? kW - k + 1 : 0; }
+
+uint64_t bucket_unit_bytes(int k)
+{
+    int S = bucket_stride_for(k);
+    return S ? 32ull * 16 * S : 0;  // one warp iteration
+}
+
+size_t bucket_table_w_bytes() { return ((size_t)1 << (2 * kW)) * sizeof(uint16_t); }
+int bucket_count() { return kNB; }
+
+cudaError_t launch_count_bucketed(const LaunchInfo &li, const BucketScratch &bs, const uint8_t *d_stream, uint64_t lo, uint64_t hi, int k,
+                                  uint32_t *d_table, uint8_t *d_flags, fkb_partials *d_partials, cudaStream_t st, int *launches)
+{
+    switch (bucket_stride_for(k)) {
+    case 1: return run_bucketed<1>(li, bs, d_stream, lo, hi, d_table, d_flags, d_partials, st, launches);
+    case 2: return run_bucketed<2>(li, bs, d_stream, lo, hi, d_table, d_flags, d_partials, st, launches);
+    case 3: return run_bucketed<3>(li, bs, d_stream, lo, hi, d_table, d_flags, d_partials, st, launches);
+    case 4: return run_bucketed<4>(li, bs, d_stream, lo, hi, d_table, d_flags, d_partials, st, launches);
+    case 5: return run_bucketed<5>(li, bs, d_stream, lo, hi, d_table, d_flags, d_partials, st, launches);
+    case 6: return run_bucketed<6>(li, bs, d_stream, lo, hi, d_table, d_flags, d_partials, st, launches);
+    case 7: return run_bucketed<7>(li, bs, d_stream, lo, hi, d_table, d_flags, d_partials, st, launches);
+    case 8: return run_bucketed<8>(li, bs, d_stream, lo, hi, d_table, d_flags, d_partials, st, launches);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace fkb

@@ -359,8 +359,8 @@ inline int grid_for(uint64_t items_per_thread_units, int sm_count, int ctas_per_
 
 }  // namespace
 
-cudaError_t launch_count(const LaunchInfo &li, const uint8_t *d_stream, uint64_t begin, uint64_t end, int k, uint32_t *d_table,
-                         uint8_t *d_flags, fkb_partials *d_partials, cudaStream_t st, int *launches)
+static cudaError_t launch_direct(const LaunchInfo &li, const uint8_t *d_stream, uint64_t begin, uint64_t end, int k, uint32_t *d_table,
+                                 uint8_t *d_flags, fkb_partials *d_partials, cudaStream_t st, int *launches)
 {
     if (end <= begin) return cudaSuccess;
     const uint64_t base = begin & ~15ull;
@@ -369,6 +369,33 @@ cudaError_t launch_count(const LaunchInfo &li, const uint8_t *d_stream, uint64_t
     count_direct_kernel<<<grid, kThreads, 0, st>>>(d_stream, begin, end, k, d_table, d_flags, d_partials);
     if (launches) ++*launches;
     return cudaGetLastError();
+}
+
+// below this many interior bytes the fixed costs of the bucketed path (1024 sub-table write-outs + the fold) lose
+// against one red per window
+constexpr uint64_t kBucketMinBytes = 96ull << 20;
+
+cudaError_t launch_count(const LaunchInfo &li, const uint8_t *d_stream, uint64_t begin, uint64_t end, int k, uint32_t *d_table,
+                         uint8_t *d_flags, fkb_partials *d_partials, cudaStream_t st, int *launches)
+{
+    if (end <= begin) return cudaSuccess;
+    const uint64_t unit = bucket_unit_bytes(k);
+    bool bucket = unit && li.bucket.gbuf && li.variant != VARIANT_DIRECT;
+    uint64_t lo = 0, hi = 0;
+    if (bucket) {
+        // interior [lo, hi): whole units, aligned in absolute stream coordinates, 16 readable bytes on both sides
+        lo = (begin + 16 + unit - 1) / unit * unit;
+        hi = end >= 16 ? (end - 16) / unit * unit : 0;
+        const uint64_t min_bytes = li.variant == VARIANT_BUCKET ? unit : kBucketMinBytes;
+        bucket = hi > lo && hi - lo >= min_bytes;
+    }
+    if (!bucket) return launch_direct(li, d_stream, begin, end, k, d_table, d_flags, d_partials, st, launches);
+    // the two edge slivers go through the direct kernel (it owns every ragged / unaligned / short-halo case)
+    cudaError_t e = launch_direct(li, d_stream, begin, lo, k, d_table, d_flags, d_partials, st, launches);
+    if (e != cudaSuccess) return e;
+    e = launch_count_bucketed(li, li.bucket, d_stream, lo, hi, k, d_table, d_flags, d_partials, st, launches);
+    if (e != cudaSuccess) return e;
+    return launch_direct(li, d_stream, hi, end, k, d_table, d_flags, d_partials, st, launches);
 }
 
 cudaError_t launch_finalize(const LaunchInfo &li, int k, const uint32_t *d_table, uint8_t *d_flags, const fkb_partials *d_partials,

@@ -10,13 +10,31 @@ namespace fkb {
 enum CountVariant : int {
     VARIANT_AUTO = 0,
     VARIANT_DIRECT = 1,   // fused encode + one red.global per window into the L2-resident table
-    VARIANT_SMEM = 2,     // fused encode + CTA-private shared-memory table, merged at the end (small k)
+    VARIANT_BUCKET = 2,   // W-mers at stride S routed through shared memory to per-bucket smem counters, then folded
+};
+
+// device scratch of VARIANT_BUCKET (owned by the context)
+struct BucketScratch {
+    uint16_t *gbuf = nullptr;      // [n_buckets][n_cta][cap_cb] routed payloads: one private segment per (bucket, pass-1 CTA)
+    uint32_t cap_cb = 0;           // items per segment (multiple of 8)
+    int n_cta = 0;                 // pass-1 grid size the layout was built for
+    uint32_t *gcount = nullptr;    // [n_buckets][n_cta] items in each segment
+    uint32_t *work = nullptr;      // pass-2 work counter
+    uint16_t *table_w = nullptr;   // [4^W] 16-bit W-mer counts
 };
 
 struct LaunchInfo {
     int sm_count;
     int variant;          // forced variant (VARIANT_AUTO = choose)
+    BucketScratch bucket; // valid when bucket.gbuf != nullptr
 };
+
+int bucket_stride_for(int k);        // S = W - k + 1 when the bucketed path supports k, else 0
+uint64_t bucket_unit_bytes(int k);   // interior granularity of the bucketed path
+size_t bucket_table_w_bytes();
+int bucket_count();
+cudaError_t launch_count_bucketed(const LaunchInfo &li, const BucketScratch &bs, const uint8_t *d_stream, uint64_t lo, uint64_t hi, int k,
+                                  uint32_t *d_table, uint8_t *d_flags, fkb_partials *d_partials, cudaStream_t st, int *launches);
 
 cudaError_t launch_count(const LaunchInfo &li, const uint8_t *d_stream, uint64_t begin, uint64_t end, int k,
                          uint32_t *d_table, uint8_t *d_flags, fkb_partials *d_partials, cudaStream_t st,

@@ -120,6 +120,10 @@ class KmerCounter:
     def launches(self) -> int:
         return int(self._lib.fkb_launch_count(self._ctx))
 
+    def set_variant(self, variant: int) -> None:
+        """0 = automatic, 1 = direct kernel only, 2 = bucketed kernels whenever k and the range allow."""
+        self._check(self._lib.fkb_set_option(self._ctx, b"variant", int(variant)))
+
     def device_info(self) -> dict:
         sm, ma, mi, hbm = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_size_t()
         self._check(self._lib.fkb_device_info(self._ctx, ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi), ctypes.byref(hbm)))

@@ -83,6 +83,10 @@ const char *fkb_last_error(const fkb_context *ctx);   /* text of the last failur
 const char *fkb_status_string(int status);
 const char *fkb_version(void);
 int fkb_device_info(fkb_context *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *hbm_bytes);
+/* Tuning knobs (tests and profiling).  "variant": 0 = choose by k and range length (default), 1 = always the
+ * direct kernel (one global red per window), 2 = the bucketed kernels whenever k and the range allow.
+ * The environment variable FKB_VARIANT sets the same knob at fkb_create time. */
+int fkb_set_option(fkb_context *ctx, const char *name, long value);
 
 /* ---- host loader: the "stream contract" of findKmer()'s outer loop (:988-1011) ----------------
  * Drops every '\n'; turns each '>'...'\n' header into ONE '>' byte; stops at the first byte 0xFF
