@@ -24,6 +24,8 @@
 // events (seqSize == k, :1044-1057; seqSize < k, :1059-1062) are derived from the validity bit masks.
 // profiles/r01_ncu_bucketize_v1_by_line.txt is the instruction profile of the first version of pass 1 that this
 // layout answers (38 % of instructions in the flush copy loop, 15 % in run-mask loops, a barrier per iteration).
+#include <type_traits>
+
 #include "fkb_kernels.cuh"
 
 namespace fkb {
@@ -33,11 +35,17 @@ namespace {
 constexpr int kW = 13;                       // counted word length
 constexpr int kBucketBits = 2 * kW - 16;     // 10
 constexpr int kNB = 1 << kBucketBits;        // 1024 buckets
-constexpr int kP1Threads = 512;
-constexpr int kP1Warps = kP1Threads / 32;
-constexpr int kStageCap = 96;                // staged items per bucket (12 chunks of 8)
-constexpr int kTileIters = 5;                // warp iterations between flushes: 5 * 8192 items / 1024 buckets = 40 avg (+ <= 7 carried)
+constexpr int kStageCap = 104;               // staged items per bucket (13 chunks of 8): 1024 rows of 208 B = 208 KiB
+constexpr int kTileItems = 64 * kNB;         // items a CTA stages between flushes: ~64 per bucket on average (+ <= 7 carried) of 104
 constexpr int kP2Threads = 1024;
+
+// pass-1 CTA size: as many warps as the register budget of the stride allows (1 CTA per SM: the staging rows take 192 KiB)
+template <int S> struct P1Cfg { static constexpr int kThreads = (S <= 3) ? 768 : 512; };
+
+// Staging rows are 208 bytes (13 chunks of 16 bytes) apart: 52 words == 20 banks, so consecutive rows start on 8
+// different bank offsets and a warp's stores (all rows fill at about the same rate) spread over all 32 banks, while
+// every chunk stays 16-byte aligned for the 128-bit flush copies.
+__device__ __forceinline__ uint32_t stage_slot(uint32_t bucket, uint32_t pos) { return bucket * kStageCap + pos; }
 
 __host__ __device__ inline uint64_t flags_offset(int d) { return ((1ull << (2 * d)) - 4ull) / 3ull; }
 
@@ -177,12 +185,54 @@ struct P1Smem {
     uint32_t goff[kNB];    // items already appended to this CTA's region of the bucket (multiple of 8 until the end)
 };
 
+// predicated shared-memory atomic / store on 32-bit shared addresses: no branches, so the 8 atomics of a batch issue
+// back to back and their latencies overlap (the compiler otherwise serialises `if (p) pos = atomicAdd(...)` chains)
+__device__ __forceinline__ uint32_t atoms_inc_if(uint32_t saddr, uint32_t pred, uint32_t if_not)
+{
+    uint32_t old = if_not;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p atom.shared.add.u32 %0, [%1], 1;\n\t}" : "+r"(old) : "r"(saddr), "r"(pred) : "memory");
+    return old;
+}
+__device__ __forceinline__ uint32_t atoms_inc(uint32_t saddr)
+{
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(saddr) : "memory");
+    return old;
+}
+__device__ __forceinline__ void sts16_if(uint32_t saddr, uint32_t value, uint32_t pred)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u16 [%0], %1;\n\t}" ::"r"(saddr), "h"((uint16_t)value), "r"(pred) : "memory");
+}
+
+// staging-row overflow of one chunk's items (bit n of `ovf` = n-th static slot): exact escape, off the hot path
 template <int S>
-__global__ void __launch_bounds__(kP1Threads, 1)
+__device__ __noinline__ void escape_slots(uint32_t ovf, const uint32_t *codes /* S+1 words: group before + own groups */, uint32_t *table_k)
+{
+    constexpr uint32_t WMASK = (1u << (2 * kW)) - 1u;
+    int n = 0;
+    for (int g = 1; g <= S; ++g)
+        for (int i = 0; i < 16; ++i) {
+            if ((16 * (g - 1) + i) % S != (kW - 1) % S) continue;
+            if (ovf & (1u << n)) red_kmers_of_word<S>(__funnelshift_r(codes[g], codes[g - 1], 2 * (15 - i)) & WMASK, table_k, 1u);
+            ++n;
+        }
+}
+
+template <int S>
+__device__ __noinline__ void escape_chunk(uint32_t bucket, uint4 v, uint32_t *table_k)
+{
+    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+    for (int e = 0; e < 8; ++e) red_kmers_of_word<S>((bucket << 16) | ((w4[e >> 1] >> (16 * (e & 1))) & 0xFFFFu), table_k, 1u);
+}
+
+template <int S>
+__global__ void __launch_bounds__(P1Cfg<S>::kThreads, 1)
 bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, uint16_t *__restrict__ gbuf, uint32_t cap_cb,
                  uint32_t *__restrict__ gcount, uint32_t *__restrict__ table_k, uint8_t *__restrict__ flags, fkb_partials *__restrict__ P)
 {
     static_assert(S >= 1 && S <= 8, "stride");
+    constexpr int kP1Threads = P1Cfg<S>::kThreads, kP1Warps = kP1Threads / 32;
+    constexpr int kTileIters = kTileItems / (kP1Threads * 16);  // warp iterations between flushes
     constexpr int K = kW - S + 1;
     constexpr int CH = 16 * S;                     // bytes per lane per iteration: exactly 16 items
     constexpr int J = S - 1;
@@ -192,6 +242,7 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
     extern __shared__ __align__(16) uint8_t smem_raw[];
     P1Smem &sm = *reinterpret_cast<P1Smem *>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t cursor_sa = (uint32_t)__cvta_generic_to_shared(sm.cursor), stage_sa = (uint32_t)__cvta_generic_to_shared(sm.stage);
 
     for (int b = threadIdx.x; b < kNB; b += kP1Threads) { sm.cursor[b] = 0; sm.goff[b] = 0; }
     __syncthreads();
@@ -211,12 +262,15 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
     // ---- software pipeline: `cur` = packed groups of iteration it, `nxt` = of it+1, `raw` = loads of it+2 in flight ----
     Group cur[S], nxt[S], carry;   // carry: the 16 bytes in front of lane 0's chunk (previous iteration's lane 31, last group)
     uint4 raw[S];
-    auto issue_loads = [&](uint64_t it) {  // iteration index it may be my_iters (only lane 0's first group: the right halo) or beyond (nothing)
+    auto issue_loads = [&](uint64_t it) {  // it == my_iters: only lane 0's first group (the right halo of the region); beyond: nothing
         const uint64_t base = region + it * WSPAN + (uint64_t)lane * CH;
+        if (it < my_iters) {
 #pragma unroll
-        for (int g = 0; g < S; ++g) {
-            const bool need = it < my_iters || (it == my_iters && lane == 0 && g == 0);
-            raw[g] = need ? ldg128(s + base + 16 * g) : make_uint4(0, 0, 0, 0);
+            for (int g = 0; g < S; ++g) raw[g] = ldg128(s + base + 16 * g);
+        } else {
+#pragma unroll
+            for (int g = 0; g < S; ++g) raw[g] = make_uint4(0, 0, 0, 0);
+            if (it == my_iters && lane == 0) raw[0] = ldg128(s + base);
         }
     };
     {
@@ -254,16 +308,11 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
             const bool edge = (cbase == lo) || (cbase + CH == hi);
 
             uint32_t emit[S + 2];
-            if (vall == 0xFFFFu && !edge) {
+            const bool all_emit = (vall == 0xFFFFu && !edge);
+            if (all_emit) {
                 // ---- fast path: 16*(S+2) valid bases around me: every anchored window exists, nothing is left over ----
 #pragma unroll
-                for (int g = 1; g <= S; ++g) {
-                    uint32_t phase = 0;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if ((16 * (g - 1) + i) % S == (kW - 1) % S) phase |= 1u << (15 - i);
-                    emit[g] = phase;
-                }
+                for (int g = 0; g < S + 2; ++g) emit[g] = 0;
                 t_windows += 16 * S;
                 t_valid += 16 * S;
             } else {
@@ -299,20 +348,49 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
                 }
             }
 
-            // ---- the 16 items of this chunk: static slots ----
+            // ---- the 16 items of this chunk: static slots (slot n ends at chunk offset (W-1)%S + n*S), two batches of 8:
+            //      8 shared atomics back to back (slot in the bucket's staging row), then 8 stores ----
+            uint32_t ovf = 0;
+            auto stage_items = [&](auto all_t) {
+                constexpr bool ALL = decltype(all_t)::value;  // every slot is emitted: no predicates at all
+                uint32_t wc[16];
 #pragma unroll
-            for (int g = 1; g <= S; ++g) {
+                for (int n = 0; n < 16; ++n) {
+                    constexpr int o0 = (kW - 1) % S;
+                    const int o = o0 + n * S, g = o / 16 + 1, i = o % 16;
+                    wc[n] = __funnelshift_r(grp[g].code, grp[g - 1].code, 2 * (15 - i)) & WMASK;
+                }
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    if ((16 * (g - 1) + i) % S != (kW - 1) % S) continue;
-                    if (emit[g] & (1u << (15 - i))) {
-                        const uint32_t wcode = __funnelshift_r(grp[g].code, grp[g - 1].code, 2 * (15 - i)) & WMASK;
-                        const uint32_t bucket = wcode >> 16;
-                        const uint32_t pos = atomicAdd(&sm.cursor[bucket], 1u);
-                        if (pos < (uint32_t)kStageCap) sm.stage[bucket * kStageCap + pos] = (uint16_t)wcode;
-                        else red_kmers_of_word<S>(wcode, table_k, 1u);  // staging row full (skewed input): exact escape
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t pos[8];
+#pragma unroll
+                    for (int n = 8 * h; n < 8 * h + 8; ++n) {
+                        constexpr int o0 = (kW - 1) % S;
+                        const int o = o0 + n * S, g = o / 16 + 1, i = o % 16;
+                        const uint32_t ca = cursor_sa + ((wc[n] >> 14) & 0xFFCu);  // &cursor[bucket]
+                        if constexpr (ALL) pos[n - 8 * h] = atoms_inc(ca);
+                        else pos[n - 8 * h] = atoms_inc_if(ca, emit[g] & (1u << (15 - i)), kStageCap);
+                    }
+#pragma unroll
+                    for (int n = 8 * h; n < 8 * h + 8; ++n) {
+                        constexpr int o0 = (kW - 1) % S;
+                        const int o = o0 + n * S, g = o / 16 + 1, i = o % 16;
+                        const uint32_t bucket = wc[n] >> 16, ps = pos[n - 8 * h];
+                        const uint32_t sa = stage_sa + bucket * (2u * kStageCap) + 2u * ps;
+                        const uint32_t fits = ps < (uint32_t)kStageCap;
+                        sts16_if(sa, wc[n], fits);
+                        const uint32_t emitted = ALL ? 1u : ((emit[g] >> (15 - i)) & 1u);
+                        ovf |= (emitted & (fits ^ 1u)) << n;
                     }
                 }
+            };
+            if (all_emit) stage_items(std::true_type{});
+            else stage_items(std::false_type{});
+            if (ovf) {  // skewed input: some staging row is full
+                uint32_t codes[S + 1];
+#pragma unroll
+                for (int g = 0; g <= S; ++g) codes[g] = grp[g].code;
+                escape_slots<S>(ovf, codes, table_k);
             }
 
             // ---- advance the pipeline ----
@@ -326,32 +404,28 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
         // ---- flush: append whole 16-byte chunks of every staged row to this CTA's region of the bucket ----
         __syncthreads();
         {
-            const int sub = lane >> 3, c = lane & 7;  // 4 buckets per warp step, 8 lanes each
-            for (int r = 0; r < kNB / kP1Warps / 4; ++r) {
-                const int b = warp * (kNB / kP1Warps) + r * 4 + sub;
+            const uint32_t sub = lane >> 3, c = lane & 7;  // 4 buckets per warp step, 8 lanes each
+            const uint64_t bstride = (uint64_t)gridDim.x * cap_cb;
+            for (uint32_t b = warp * 4 + sub; b < (uint32_t)kNB; b += kP1Warps * 4) {
                 const uint32_t cnt = min(sm.cursor[b], (uint32_t)kStageCap);
                 const uint32_t n8 = cnt & ~7u, off = sm.goff[b];
                 uint16_t *row = &sm.stage[b * kStageCap];
-                uint16_t *dst = my_gbuf + (uint64_t)b * gridDim.x * cap_cb + off;
+                uint16_t *dst = my_gbuf + b * bstride + off;
                 uint4 tail = make_uint4(0, 0, 0, 0);
-                if (c == 0 && n8 && cnt > n8) tail = *reinterpret_cast<const uint4 *>(row + n8);  // the <= 7 items that stay staged
+                const bool has_tail = (c == 0) && n8 && cnt > n8;
+                if (has_tail) tail = *reinterpret_cast<const uint4 *>(row + n8);  // the <= 7 items that stay staged
 #pragma unroll
                 for (int cc = 0; cc < 2; ++cc) {
-                    const uint32_t i0 = (uint32_t)(c + 8 * cc) * 8u;
+                    const uint32_t ci = c + 8 * cc, i0 = ci * 8u;
                     if (i0 < n8) {
                         const uint4 v = *reinterpret_cast<const uint4 *>(row + i0);
-                        if (off + i0 + 8 <= cap_cb) {
-                            *reinterpret_cast<uint4 *>(dst + i0) = v;
-                        } else {  // this CTA's region of the bucket is full (heavily skewed input): exact escape
-                            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-                            for (int e = 0; e < 8; ++e)
-                                red_kmers_of_word<S>(((uint32_t)b << 16) | ((w4[e >> 1] >> (16 * (e & 1))) & 0xFFFFu), table_k, 1u);
-                        }
+                        if (off + i0 + 8 <= cap_cb) *reinterpret_cast<uint4 *>(dst + i0) = v;
+                        else escape_chunk<S>(b, v, table_k);  // this CTA's region of the bucket is full (heavily skewed input)
                     }
                 }
                 __syncwarp();
                 if (c == 0) {
-                    if (n8 && cnt > n8) *reinterpret_cast<uint4 *>(row) = tail;
+                    if (has_tail) *reinterpret_cast<uint4 *>(row) = tail;
                     sm.cursor[b] = cnt - n8;
                     sm.goff[b] = min(off + n8, cap_cb & ~7u);
                 }
@@ -366,7 +440,7 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
         uint32_t off = sm.goff[b];
         uint16_t *dst = my_gbuf + (uint64_t)b * gridDim.x * cap_cb;
         for (uint32_t i = 0; i < cnt; ++i) {
-            const uint16_t item = sm.stage[b * kStageCap + i];
+            const uint16_t item = sm.stage[stage_slot(b, i)];
             if (off < cap_cb) dst[off++] = item;
             else red_kmers_of_word<S>(((uint32_t)b << 16) | item, table_k, 1u);
         }
@@ -426,12 +500,20 @@ count_buckets_kernel(const uint16_t *__restrict__ gbuf, uint32_t cap_cb, const u
             const uint32_t n = min(gcount[(uint64_t)b * n_seg + seg], cap_cb);
             const uint16_t *items = gbuf + ((uint64_t)b * n_seg + seg) * cap_cb;  // 16-byte aligned: cap_cb is a multiple of 8
             const uint32_t n8 = n & ~7u;
-            for (uint32_t i = lane * 8u; i < n8; i += 256u) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(items + i);
-                add_item(v.x & 0xFFFFu); add_item(v.x >> 16);
-                add_item(v.y & 0xFFFFu); add_item(v.y >> 16);
-                add_item(v.z & 0xFFFFu); add_item(v.z >> 16);
-                add_item(v.w & 0xFFFFu); add_item(v.w >> 16);
+            for (uint32_t i = lane * 8u; i < n8; i += 1024u) {  // four 128-bit loads in flight per lane
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    v[u] = (i + 256u * u < n8) ? *reinterpret_cast<const uint4 *>(items + i + 256u * u) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (i + 256u * u < n8) {
+                        add_item(v[u].x & 0xFFFFu); add_item(v[u].x >> 16);
+                        add_item(v[u].y & 0xFFFFu); add_item(v[u].y >> 16);
+                        add_item(v[u].z & 0xFFFFu); add_item(v[u].z >> 16);
+                        add_item(v[u].w & 0xFFFFu); add_item(v[u].w >> 16);
+                    }
+                }
             }
             if ((uint32_t)lane < n - n8) add_item(items[n8 + lane]);
         }
@@ -482,7 +564,7 @@ cudaError_t run_bucketed(const LaunchInfo &li, const BucketScratch &bs, const ui
     const uint64_t n_witers = (hi - lo) / wspan;
     cudaError_t e = cudaMemsetAsync(bs.work, 0, 16, st);
     if (e != cudaSuccess) return e;
-    bucketize_kernel<S><<<bs.n_cta, kP1Threads, sizeof(P1Smem), st>>>(d_stream, lo, n_witers, bs.gbuf, bs.cap_cb, bs.gcount, d_table, d_flags, d_partials);
+    bucketize_kernel<S><<<bs.n_cta, P1Cfg<S>::kThreads, sizeof(P1Smem), st>>>(d_stream, lo, n_witers, bs.gbuf, bs.cap_cb, bs.gcount, d_table, d_flags, d_partials);
     count_buckets_kernel<S><<<li.sm_count, kP2Threads, 128 * 1024, st>>>(bs.gbuf, bs.cap_cb, bs.gcount, bs.n_cta, bs.table_w, d_table, bs.work);
     constexpr int K = kW - S + 1;
     const uint64_t n = 1ull << (2 * K);
