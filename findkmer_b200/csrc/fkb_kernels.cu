@@ -141,10 +141,13 @@ __device__ __forceinline__ void scan_word(Scan &s, uint32_t w, uint32_t mask, in
 // VARIANT_DIRECT: fused encode + count, one red.global.add.u32 per window.
 // The 4^k table (16 MiB at k = 11) is L2-resident; the atomics never reach HBM.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) count_direct_kernel(const uint8_t *__restrict__ s, uint64_t begin, uint64_t end, int k,
-                                                                uint32_t *__restrict__ table, uint8_t *__restrict__ flags,
+// A second range [begin2, end2) may ride along (blockIdx.y == 1): the two edge slivers around a bucketed interior.
+__global__ void __launch_bounds__(kThreads) count_direct_kernel(const uint8_t *__restrict__ s, uint64_t begin, uint64_t end, uint64_t begin2,
+                                                                uint64_t end2, int k, uint32_t *__restrict__ table, uint8_t *__restrict__ flags,
                                                                 fkb_partials *__restrict__ P)
 {
+    if (blockIdx.y == 1) { begin = begin2; end = end2; }
+    if (end <= begin) return;
     const uint32_t mask = (k == 16) ? 0xffffffffu : ((1u << (2 * k)) - 1u);
     const uint64_t base = begin & ~15ull;                      // chunks are 16-byte aligned in the stream
     const uint64_t n_chunks = (end - base + kChunk - 1) / kChunk;
@@ -212,16 +215,18 @@ __global__ void __launch_bounds__(kThreads) finalize_table_kernel(const uint32_t
         nodes += (v.x != 0) + (v.y != 0) + (v.z != 0) + (v.w != 0);
         if (k > 1 && sum != 0) flags[flags_offset(k - 1) + g] = 1;
     }
-    tot = warp_sum(tot); nodes = warp_sum(nodes);
+    // block-level reduction: one set of 10 global atomics per CTA instead of per warp (they all hit the same 10 words)
+    unsigned long long vals[10] = {tot, last[0], last[1], last[2], last[3], first[0], first[1], first[2], first[3], nodes};
+    __shared__ unsigned long long red[kThreads / 32][10];
 #pragma unroll
-    for (int b = 0; b < 4; ++b) { last[b] = warp_sum(last[b]); first[b] = warp_sum(first[b]); }
-    if ((threadIdx.x & 31) == 0) {
-        if (tot) atomicAdd(&scratch[0], tot);
-        for (int b = 0; b < 4; ++b) {
-            if (last[b]) atomicAdd(&scratch[1 + b], last[b]);
-            if (first[b]) atomicAdd(&scratch[5 + b], first[b]);
-        }
-        if (nodes) atomicAdd(&scratch[9], nodes);
+    for (int i = 0; i < 10; ++i) vals[i] = warp_sum(vals[i]);
+    if ((threadIdx.x & 31) == 0)
+        for (int i = 0; i < 10; ++i) red[threadIdx.x >> 5][i] = vals[i];
+    __syncthreads();
+    if (threadIdx.x < 10) {
+        unsigned long long v = 0;
+        for (int w = 0; w < kThreads / 32; ++w) v += red[w][threadIdx.x];
+        if (v) atomicAdd(&scratch[threadIdx.x], v);
     }
 }
 
@@ -359,14 +364,14 @@ inline int grid_for(uint64_t items_per_thread_units, int sm_count, int ctas_per_
 
 }  // namespace
 
-static cudaError_t launch_direct(const LaunchInfo &li, const uint8_t *d_stream, uint64_t begin, uint64_t end, int k, uint32_t *d_table,
-                                 uint8_t *d_flags, fkb_partials *d_partials, cudaStream_t st, int *launches)
+static cudaError_t launch_direct(const LaunchInfo &li, const uint8_t *d_stream, uint64_t begin, uint64_t end, uint64_t begin2, uint64_t end2,
+                                 int k, uint32_t *d_table, uint8_t *d_flags, fkb_partials *d_partials, cudaStream_t st, int *launches)
 {
-    if (end <= begin) return cudaSuccess;
-    const uint64_t base = begin & ~15ull;
-    const uint64_t n_chunks = (end - base + kChunk - 1) / kChunk;
-    int grid = grid_for(n_chunks, li.sm_count, 8);
-    count_direct_kernel<<<grid, kThreads, 0, st>>>(d_stream, begin, end, k, d_table, d_flags, d_partials);
+    const uint64_t len1 = end > begin ? end - (begin & ~15ull) : 0, len2 = end2 > begin2 ? end2 - (begin2 & ~15ull) : 0;
+    const uint64_t longest = len1 > len2 ? len1 : len2;
+    if (!longest) return cudaSuccess;
+    dim3 grid((unsigned)grid_for((longest + kChunk - 1) / kChunk, li.sm_count, 8), len2 ? 2 : 1);
+    count_direct_kernel<<<grid, kThreads, 0, st>>>(d_stream, begin, end, begin2, end2, k, d_table, d_flags, d_partials);
     if (launches) ++*launches;
     return cudaGetLastError();
 }
@@ -389,13 +394,11 @@ cudaError_t launch_count(const LaunchInfo &li, const uint8_t *d_stream, uint64_t
         const uint64_t min_bytes = li.variant == VARIANT_BUCKET ? unit : kBucketMinBytes;
         bucket = hi > lo && hi - lo >= min_bytes;
     }
-    if (!bucket) return launch_direct(li, d_stream, begin, end, k, d_table, d_flags, d_partials, st, launches);
-    // the two edge slivers go through the direct kernel (it owns every ragged / unaligned / short-halo case)
-    cudaError_t e = launch_direct(li, d_stream, begin, lo, k, d_table, d_flags, d_partials, st, launches);
+    if (!bucket) return launch_direct(li, d_stream, begin, end, 0, 0, k, d_table, d_flags, d_partials, st, launches);
+    // the two edge slivers go through the direct kernel (it owns every ragged / unaligned / short-halo case), in one launch
+    cudaError_t e = launch_direct(li, d_stream, begin, lo, hi, end, k, d_table, d_flags, d_partials, st, launches);
     if (e != cudaSuccess) return e;
-    e = launch_count_bucketed(li, li.bucket, d_stream, lo, hi, k, d_table, d_flags, d_partials, st, launches);
-    if (e != cudaSuccess) return e;
-    return launch_direct(li, d_stream, hi, end, k, d_table, d_flags, d_partials, st, launches);
+    return launch_count_bucketed(li, li.bucket, d_stream, lo, hi, k, d_table, d_flags, d_partials, st, launches);
 }
 
 cudaError_t launch_finalize(const LaunchInfo &li, int k, const uint32_t *d_table, uint8_t *d_flags, const fkb_partials *d_partials,
