@@ -153,13 +153,6 @@ def workload_config(args, extra=None):
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
-def shard_cuts(total: int, world: int):
-    """contiguous byte ranges with 16-byte aligned cut points"""
-    cuts = [((total * r // world) + 15) // 16 * 16 for r in range(world)] + [total]
-    cuts[0] = 0
-    return cuts
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -184,6 +177,7 @@ def main():
     import torch.distributed as dist
     from findkmer_b200 import synth
     from findkmer_b200.engine import KmerCounter
+    from findkmer_b200.sharded import reduce_accumulators, shard_cuts
     from findkmer_b200._lib import FkbCounts
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -225,10 +219,7 @@ def main():
         torch.cuda.synchronize()
 
     def reduce_acc():
-        if world > 1:
-            dist.reduce(acc.table, 0, op=dist.ReduceOp.SUM)
-            dist.reduce(acc.flags, 0, op=dist.ReduceOp.MAX)
-            dist.reduce(acc.partials, 0, op=dist.ReduceOp.SUM)
+        reduce_accumulators(acc.table, acc.flags, acc.partials, dst=0)
 
     ev_pairs = []
 
