@@ -9,7 +9,7 @@ One "step" = one pass of the counting hot path over the whole workload (config 4
     value : stripped stream already resident in HBM -> zero accumulators, count kernel(s), [NCCL reduce],
             finalize (N, base counts, node count); timed with CUDA events, max over ranks.
     e2e   : the same job through the host-buffer C-ABI call -- raw FASTA bytes in PINNED HOST memory ->
-            host strip threads -> H2D -> kernels -> [reduce] -> finalize -> table + counts back on the host.
+            H2D -> device strip -> kernels -> [reduce] -> finalize -> table + counts back on the host.
 Strong scaling: the 3.1 Gbp are split into N contiguous shards (16-byte halo), one per GPU; per-GPU tables
 are summed with one NCCL reduce (plus a max-reduce of the prefix flags and a sum of 12 scalars).
 """
@@ -303,13 +303,13 @@ def main():
             nonlocal h2d, d2h
             if world == 1:
                 counter._check(lib.fkb_count_fasta_host(ctx, h_raw.data_ptr(), h_raw.numel(), k, h_table.data_ptr(), ctypes.byref(h_counts)))
-                h2d = h_counts.stream_bytes + 16
+                h2d = h_raw.numel() + 64  # pinned input: the raw file bytes cross PCIe once and are stripped on the GPU
                 d2h = h_table.numel() * 4 + ctypes.sizeof(FkbCounts)
                 return
             counter._check(lib.fkb_zero_device(ctx, k, acc.table.data_ptr(), acc.flags.data_ptr(), acc.partials.data_ptr(), st.cuda_stream))
             torch.cuda.synchronize()
             sb, stop, eih = counter.count_fasta_range(h_raw, look, k, acc)
-            h2d = sb + 16
+            h2d = h_raw.numel() - look + 64
             reduce_acc()
             if rank == 0:
                 counter._check(lib.fkb_finalize_device(ctx, k, acc.table.data_ptr(), acc.flags.data_ptr(), acc.partials.data_ptr(),
@@ -338,7 +338,8 @@ def main():
             assert int(h_table.to(torch.int64).sum()) == expect
         e2e = {"value": args.bases / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps,
-               "path": "pinned host FASTA bytes -> host strip threads -> H2D -> count -> finalize -> table+counts D2H"}
+               "path": "raw FASTA bytes in pinned host memory -> H2D in 128 MiB chunks -> device strip (record/line compaction) -> "
+                       "count -> [reduce] -> finalize -> table + counts D2H; pageable inputs use the host loader threads instead"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

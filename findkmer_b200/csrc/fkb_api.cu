@@ -51,6 +51,15 @@ struct fkb_context {
 
     fkb::BucketScratch bucket;  // scratch of the bucketed count path (grown on demand)
 
+    // device-side loader (pinned inputs): two raw chunk buffers, tile scratch, the chained strip state
+    int loader_mode = 0;  // 0 = auto (pinned input -> device strip, pageable -> host strip), 1 = host strip, 2 = device strip
+    size_t loader_chunk = 0;  // raw bytes per device-loader chunk (0 = kRawChunkBytes); tests shrink it to cross chunk edges
+    uint8_t *d_raw[2] = {nullptr, nullptr};
+    void *d_strip_scratch = nullptr;
+    void *d_strip_state = nullptr;
+    void *h_strip_state = nullptr;  // pinned
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_strip[2] = {nullptr, nullptr};
+
     // pinned staging ring for the loader
     static constexpr int kSlots = 12;
     size_t slot_bytes = 0;
@@ -61,6 +70,7 @@ struct fkb_context {
 namespace {
 
 constexpr size_t kBlockBytes = 4u << 20;  // loader block: 4 MiB of raw file per strip task
+constexpr size_t kRawChunkBytes = 128u << 20;  // device loader: raw bytes per H2D copy / strip launch
 
 int fail(fkb_context *ctx, int status, const char *fmt, ...)
 {
@@ -179,6 +189,110 @@ int finish_host(fkb_context *ctx, int k, uint64_t stream_bytes, uint32_t *table,
 
 }  // namespace
 
+// left halo of a shard: the last 16 stripped bytes in front of buf[own_offset] (zeros = reset bytes at the start of a file).
+// Returns false (and the stop offset) when a byte 0xFF outside a header already ended the scan inside the look-back context.
+static bool left_halo(const uint8_t *fasta, size_t own_offset, uint8_t halo[16], uint64_t *stop_offset)
+{
+    memset(halo, 0, 16);
+    if (own_offset == 0) return true;
+    size_t look = 256;
+    std::vector<uint8_t> tmp;
+    for (;;) {
+        size_t lb = own_offset > look ? own_offset - look : 0;
+        tmp.assign(own_offset - lb + 64, 0);
+        fkb::StripResult r = fkb::strip_block(fasta, lb, own_offset, fkb::in_header_at(fasta, lb), tmp.data());
+        if (r.stop_pos != SIZE_MAX) {
+            *stop_offset = r.stop_pos;
+            return false;
+        }
+        if (r.n_out >= 16 || lb == 0) {
+            size_t n = r.n_out < 16 ? r.n_out : 16;
+            memcpy(halo + 16 - n, tmp.data() + r.n_out - n, n);
+            return true;
+        }
+        look *= 8;
+    }
+}
+
+// Device loader over buf[own_offset, len) for PINNED input: the raw bytes cross PCIe in 128 MiB chunks (two device
+// buffers, copy engine on its own stream), each chunk is stripped on the GPU (fkb_strip.cu) straight into the device
+// stream and the newly completed byte range is counted -- the host only launches, it never touches the data.
+static int pipeline_range_device(fkb_context *ctx, const uint8_t *fasta, size_t len, size_t own_offset, int k, uint32_t *d_table,
+                                 uint8_t *d_flags, fkb_partials *d_partials, uint64_t *stream_bytes, uint64_t *stop_offset, int *ends_in_header_out)
+{
+    *stream_bytes = 0;
+    *stop_offset = UINT64_MAX;
+    *ends_in_header_out = 0;
+    if (int s = ensure_stream(ctx, (len - own_offset) + 16 + 64)) return s;
+    if (!ctx->d_raw[0]) {
+        for (int i = 0; i < 2; ++i) {
+            FKB_CUDA(ctx, cudaMalloc(&ctx->d_raw[i], kRawChunkBytes + 64));
+            FKB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
+            FKB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_strip[i], cudaEventDisableTiming));
+        }
+        FKB_CUDA(ctx, cudaMalloc(&ctx->d_strip_scratch, fkb::strip_scratch_bytes(kRawChunkBytes)));
+        FKB_CUDA(ctx, cudaMalloc(&ctx->d_strip_state, 64));
+        FKB_CUDA(ctx, cudaHostAlloc(&ctx->h_strip_state, 64, cudaHostAllocDefault));
+    }
+    uint8_t halo[16];
+    if (!left_halo(fasta, own_offset, halo, stop_offset)) return FKB_OK;  // the scan ended before this shard begins
+    fkb::strip_state_init(ctx->h_strip_state, 16, fkb::in_header_at(fasta, own_offset) ? 1 : 0);
+    FKB_CUDA(ctx, cudaMemcpyAsync(ctx->d_stream, halo, 16, cudaMemcpyHostToDevice, ctx->s_pipe));
+    FKB_CUDA(ctx, cudaMemcpyAsync(ctx->d_strip_state, ctx->h_strip_state, fkb::strip_state_bytes(), cudaMemcpyHostToDevice, ctx->s_pipe));
+    FKB_CUDA(ctx, cudaStreamSynchronize(ctx->s_pipe));  // halo[] is a stack buffer; also orders the state before the copy stream's work
+
+    const size_t span = len - own_offset;
+    const size_t chunk = ctx->loader_chunk ? ctx->loader_chunk : kRawChunkBytes;
+    const size_t n_chunks = (span + chunk - 1) / chunk;
+    auto issue_copy = [&](size_t c) -> cudaError_t {
+        const int slot = (int)(c & 1);
+        const size_t a = own_offset + c * chunk, n = (a + chunk <= len) ? chunk : len - a;
+        cudaError_t e = cudaSuccess;
+        if (c >= 2) e = cudaStreamWaitEvent(ctx->s_aux, ctx->ev_strip[slot], 0);  // the buffer's previous chunk has been consumed
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_raw[slot], fasta + a, n, cudaMemcpyHostToDevice, ctx->s_aux);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_copy[slot], ctx->s_aux);
+        return e;
+    };
+    uint64_t counted = 16, out_off = 16, stop = UINT64_MAX;
+    int in_header = 0;
+    FKB_CUDA(ctx, issue_copy(0));
+    for (size_t c = 0; c < n_chunks; ++c) {
+        if (c + 1 < n_chunks) FKB_CUDA(ctx, issue_copy(c + 1));  // keep PCIe busy while this chunk is stripped and counted
+        const int slot = (int)(c & 1);
+        const size_t a = own_offset + c * chunk, n = (a + chunk <= len) ? chunk : len - a;
+        FKB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_pipe, ctx->ev_copy[slot], 0));
+        int launches = 0;
+        FKB_CUDA(ctx, fkb::launch_strip_chunk(ctx->d_raw[slot], n, a, ctx->d_strip_state, ctx->d_strip_scratch, ctx->d_stream, ctx->s_pipe, &launches));
+        FKB_CUDA(ctx, cudaEventRecord(ctx->ev_strip[slot], ctx->s_pipe));
+        FKB_CUDA(ctx, cudaMemcpyAsync(ctx->h_strip_state, ctx->d_strip_state, fkb::strip_state_bytes(), cudaMemcpyDeviceToHost, ctx->s_pipe));
+        FKB_CUDA(ctx, cudaStreamSynchronize(ctx->s_pipe));
+        fkb::strip_state_read(ctx->h_strip_state, &out_off, &stop, &in_header);
+        const bool last = (c + 1 == n_chunks) || stop != UINT64_MAX;
+        if (out_off > counted && (last || out_off - counted >= (96ull << 20))) {
+            cudaError_t e = fkb::launch_count(launch_info(ctx), ctx->d_stream, counted, out_off, k, d_table, d_flags, d_partials, ctx->s_pipe, &launches);
+            counted = out_off;
+            FKB_CUDA(ctx, e);
+        }
+        ctx->launches += launches;
+        if (stop != UINT64_MAX) break;
+    }
+    FKB_CUDA(ctx, cudaStreamSynchronize(ctx->s_aux));  // a copy issued ahead of a stop must not outlive the call
+    *stream_bytes = out_off - 16;
+    if (stop != UINT64_MAX) *stop_offset = stop;
+    else *ends_in_header_out = in_header;
+    return FKB_OK;
+}
+
+static bool is_pinned_host(const void *p)
+{
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
+}
+
 // Loader pipeline over buf[own_offset, len): host threads strip 4 MiB blocks into pinned slots; this thread
 // commits the blocks IN ORDER -- H2D copy to the running offset in the device stream, then a count kernel over
 // the newly arrived byte range (its left halo is already there) -- and recycles a slot when its copy is done.
@@ -187,34 +301,17 @@ int finish_host(fkb_context *ctx, int k, uint64_t stream_bytes, uint32_t *table,
 static int pipeline_range(fkb_context *ctx, const uint8_t *fasta, size_t len, size_t own_offset, int k, uint32_t *d_table, uint8_t *d_flags,
                           fkb_partials *d_partials, uint64_t *stream_bytes, uint64_t *stop_offset, int *ends_in_header_out)
 {
+    // pinned file image: let the GPU strip it (no host pass); pageable memory has to be touched by the CPU anyway
+    if (ctx->loader_mode == 2 || (ctx->loader_mode == 0 && is_pinned_host(fasta)))
+        return pipeline_range_device(ctx, fasta, len, own_offset, k, d_table, d_flags, d_partials, stream_bytes, stop_offset, ends_in_header_out);
     *stream_bytes = 0;
     *stop_offset = UINT64_MAX;
     *ends_in_header_out = 0;
     if (int s = ensure_stream(ctx, (len - own_offset) + 16 + 64)) return s;
     if (int s = ensure_slots(ctx)) return s;
 
-    // ---- left halo ----
     uint8_t halo[16];
-    memset(halo, 0, sizeof halo);
-    if (own_offset > 0) {
-        size_t look = 256;
-        std::vector<uint8_t> tmp;
-        for (;;) {
-            size_t lb = own_offset > look ? own_offset - look : 0;
-            tmp.assign(own_offset - lb + 64, 0);
-            fkb::StripResult r = fkb::strip_block(fasta, lb, own_offset, fkb::in_header_at(fasta, lb), tmp.data());
-            if (r.stop_pos != SIZE_MAX) {  // the scan ended before this shard begins: it owns nothing
-                *stop_offset = r.stop_pos;
-                return FKB_OK;
-            }
-            if (r.n_out >= 16 || lb == 0) {
-                size_t n = r.n_out < 16 ? r.n_out : 16;
-                memcpy(halo + 16 - n, tmp.data() + r.n_out - n, n);
-                break;
-            }
-            look *= 8;
-        }
-    }
+    if (!left_halo(fasta, own_offset, halo, stop_offset)) return FKB_OK;  // the scan ended before this shard begins: it owns nothing
     FKB_CUDA(ctx, cudaMemcpyAsync(ctx->d_stream, halo, 16, cudaMemcpyHostToDevice, ctx->s_pipe));
     FKB_CUDA(ctx, cudaStreamSynchronize(ctx->s_pipe));  // halo[] is a stack buffer
 
@@ -382,6 +479,8 @@ int fkb_create(int device, fkb_context **out)
     }
     const char *v = getenv("FKB_VARIANT");
     ctx->forced_variant = v ? atoi(v) : 0;
+    const char *l = getenv("FKB_LOADER");
+    ctx->loader_mode = l ? (!strcmp(l, "host") ? 1 : (!strcmp(l, "device") ? 2 : 0)) : 0;
     bool ok = cudaStreamCreateWithFlags(&ctx->s_pipe, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking) == cudaSuccess &&
               cudaMalloc(&ctx->d_scratch, sizeof(unsigned long long) * fkb::kFinalizeScratchWords) == cudaSuccess &&
@@ -404,6 +503,14 @@ void fkb_destroy(fkb_context *ctx)
         if (ctx->slots[i]) cudaFreeHost(ctx->slots[i]);
         if (ctx->slot_free[i]) cudaEventDestroy(ctx->slot_free[i]);
     }
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->d_raw[i]) cudaFree(ctx->d_raw[i]);
+        if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
+        if (ctx->ev_strip[i]) cudaEventDestroy(ctx->ev_strip[i]);
+    }
+    if (ctx->d_strip_scratch) cudaFree(ctx->d_strip_scratch);
+    if (ctx->d_strip_state) cudaFree(ctx->d_strip_state);
+    if (ctx->h_strip_state) cudaFreeHost(ctx->h_strip_state);
     if (ctx->bucket.gbuf) cudaFree(ctx->bucket.gbuf);
     if (ctx->bucket.gcount) cudaFree(ctx->bucket.gcount);
     if (ctx->bucket.work) cudaFree(ctx->bucket.work);
@@ -439,6 +546,14 @@ int fkb_set_option(fkb_context *ctx, const char *name, long value)
     if (!ctx || !name) return FKB_ERR_BAD_ARG;
     if (!strcmp(name, "variant") && value >= 0 && value <= 2) {
         ctx->forced_variant = (int)value;
+        return FKB_OK;
+    }
+    if (!strcmp(name, "loader") && value >= 0 && value <= 2) {
+        ctx->loader_mode = (int)value;
+        return FKB_OK;
+    }
+    if (!strcmp(name, "loader_chunk") && value >= 0 && (size_t)value <= kRawChunkBytes) {
+        ctx->loader_chunk = (size_t)value;
         return FKB_OK;
     }
     return fail(ctx, FKB_ERR_BAD_ARG, "unknown option %s=%ld", name, value);

@@ -49,6 +49,14 @@ cudaError_t launch_synth(const LaunchInfo &li, uint8_t *d_out, uint64_t first_by
                          int header_len, int line_width, uint64_t seed, int n_runs, int soft_mask,
                          cudaStream_t st, int *launches);
 
+// device-side strip (fkb_strip.cu): the stream contract as a chunked stream compaction
+size_t strip_scratch_bytes(uint64_t chunk_bytes);
+size_t strip_state_bytes();
+void strip_state_init(void *host_state, uint64_t out_off, int in_header);
+void strip_state_read(const void *host_state, uint64_t *out_off, uint64_t *stop_pos, int *in_header);
+cudaError_t launch_strip_chunk(const uint8_t *d_raw, uint64_t n, uint64_t chunk_pos, void *d_state, void *d_scratch, uint8_t *d_out,
+                               cudaStream_t st, int *launches);
+
 // number of unsigned long long words launch_finalize needs in d_scratch
 constexpr int kFinalizeScratchWords = 16;
 

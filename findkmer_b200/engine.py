@@ -124,6 +124,13 @@ class KmerCounter:
         """0 = automatic, 1 = direct kernel only, 2 = bucketed kernels whenever k and the range allow."""
         self._check(self._lib.fkb_set_option(self._ctx, b"variant", int(variant)))
 
+    def set_loader(self, mode: int) -> None:
+        """0 = automatic (pinned input -> device strip, pageable -> host strip threads), 1 = host loader, 2 = device loader."""
+        self._check(self._lib.fkb_set_option(self._ctx, b"loader", int(mode)))
+
+    def set_loader_chunk(self, nbytes: int) -> None:
+        self._check(self._lib.fkb_set_option(self._ctx, b"loader_chunk", int(nbytes)))
+
     def device_info(self) -> dict:
         sm, ma, mi, hbm = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_size_t()
         self._check(self._lib.fkb_device_info(self._ctx, ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi), ctypes.byref(hbm)))

@@ -85,7 +85,10 @@ const char *fkb_version(void);
 int fkb_device_info(fkb_context *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *hbm_bytes);
 /* Tuning knobs (tests and profiling).  "variant": 0 = choose by k and range length (default), 1 = always the
  * direct kernel (one global red per window), 2 = the bucketed kernels whenever k and the range allow.
- * The environment variable FKB_VARIANT sets the same knob at fkb_create time. */
+ * The environment variable FKB_VARIANT sets the same knob at fkb_create time.
+ * "loader": 0 = pinned host input is stripped on the GPU, pageable input by the host loader threads (default),
+ * 1 = always the host loader, 2 = always the device loader (FKB_LOADER=host|device).
+ * "loader_chunk": raw bytes per device-loader chunk (0 = 128 MiB). */
 int fkb_set_option(fkb_context *ctx, const char *name, long value);
 
 /* ---- host loader: the "stream contract" of findKmer()'s outer loop (:988-1011) ----------------

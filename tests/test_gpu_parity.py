@@ -243,6 +243,78 @@ def test_bucketed_and_direct_agree_on_config2(counter, harness):
         assert_counts_equal(b, harness.oracle_count_stream(stream, k))
 
 
+# ---- the device loader (stream compaction on the GPU; used automatically for pinned inputs) ------------------
+@pytest.fixture()
+def device_loader(counter):
+    counter.set_loader(2)
+    yield counter
+    counter.set_loader(0)
+    counter.set_loader_chunk(0)
+
+
+def test_device_loader_golden_and_micro_vectors(device_loader, harness, golden, test_txt):
+    from findkmer_b200 import FindKmerError, _lib
+    for k in (1, 6, 11):
+        assert_counts_equal(device_loader.count_fasta(test_txt, k), harness.oracle_count_fasta(test_txt, k))
+    for rec in golden["micro"]:
+        data = rec["input_latin1"].encode("latin1")
+        k = rec["k"]
+        if rec["hung"] or data == b"":
+            with pytest.raises(FindKmerError) as e:
+                device_loader.count_fasta(data, k)
+            assert e.value.status == (_lib.FKB_ERR_UNTERMINATED_HEADER if rec["hung"] else _lib.FKB_ERR_EMPTY_INPUT)
+            continue
+        assert_counts_equal(device_loader.count_fasta(data, k), harness.oracle_count_fasta(data, k))
+
+
+@pytest.mark.parametrize("chunk", [0, 4096, 1 << 20, (1 << 20) + 4096 + 16, 777_777])
+def test_device_loader_chunk_chaining(device_loader, harness, chunk):
+    """headers, blank lines, CRLF and junk crossing tile (4 KiB) and chunk edges; then a 0xFF that ends the scan"""
+    device_loader.set_loader_chunk(chunk)
+    data = bytearray(random_fasta(31, 3_000_000))
+    for edge in (4096, 8192, 1 << 20, 2 << 20):
+        data[edge - 30:edge + 30] = b">a header line that straddles the edge ACGT >> still header\nACGT"[:60]
+    data = bytes(data)
+    for k in (3, 11):
+        assert_counts_equal(device_loader.count_fasta(data, k), harness.oracle_count_fasta(data, k))
+    cut = bytearray(data)
+    cut[(1 << 20) + 10] = 0xFF   # inside the straddling header: skipped like any header byte
+    cut[2_500_001] = 0xFF        # (almost surely) outside a header: ends the scan
+    want = harness.oracle_count_fasta(bytes(cut), 8)
+    assert want.bytes_read < len(cut)
+    assert_counts_equal(device_loader.count_fasta(bytes(cut), 8), want)
+
+
+def test_device_loader_equals_host_loader_on_configs(counter, harness):
+    from findkmer_b200 import synth
+    for lay in (synth.config2(n_bases=5_000_000), synth.config3(n_records=3000), synth.config5(n_bases=4_000_000)):
+        data = synth.render(lay)
+        counter.set_loader(1)
+        a = counter.count_fasta(data, 9)
+        counter.set_loader(2)
+        b = counter.count_fasta(data, 9)
+        counter.set_loader(0)
+        assert np.array_equal(a.table, b.table) and a.stream_bytes == b.stream_bytes
+        assert (a.n_kmers, a.base_count, a.node_count, a.unknown_chars) == (b.n_kmers, b.base_count, b.node_count, b.unknown_chars)
+        assert_counts_equal(b, harness.oracle_count_fasta(data, 9))
+
+
+def test_device_loader_range_shards(device_loader, harness):
+    from findkmer_b200 import synth
+    data = synth.render(synth.config5(n_bases=3_000_000))
+    want = harness.oracle_count_fasta(data, 8)
+    acc = device_loader.new_accumulators(8)
+    n = len(data)
+    cuts = [0, n // 3 + 17, 2 * n // 3 + 5, n]
+    total = 0
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        lb = max(0, a - 70000)
+        sb, stop, eih = device_loader.count_fasta_range(data[lb:b], a - lb, 8, acc)
+        assert stop is None
+        total += sb
+    assert_counts_equal(device_loader.finalize_device(acc, total), want)
+
+
 # ---- loader / generator twins ---------------------------------------------------------------------------
 def test_device_generator_is_bit_identical_to_numpy(counter):
     from findkmer_b200 import synth
