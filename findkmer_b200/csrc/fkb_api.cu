@@ -116,6 +116,7 @@ int ensure_bucket_scratch(fkb_context *ctx, int k, uint64_t range_bytes)
         FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.work, 64));
     }
     if (!ctx->bucket.table_w) FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.table_w, fkb::bucket_table_w_bytes()));
+    if (!ctx->bucket.fold) FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.fold, fkb::bucket_fold_bytes()));
     FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.gbuf, nb * n_cta * cap * sizeof(uint16_t)));
     ctx->bucket.cap_cb = (uint32_t)cap;
     return FKB_OK;
@@ -515,6 +516,7 @@ void fkb_destroy(fkb_context *ctx)
     if (ctx->bucket.gcount) cudaFree(ctx->bucket.gcount);
     if (ctx->bucket.work) cudaFree(ctx->bucket.work);
     if (ctx->bucket.table_w) cudaFree(ctx->bucket.table_w);
+    if (ctx->bucket.fold) cudaFree(ctx->bucket.fold);
     if (ctx->d_stream) cudaFree(ctx->d_stream);
     if (ctx->d_table) cudaFree(ctx->d_table);
     if (ctx->d_flags) cudaFree(ctx->d_flags);

@@ -47,7 +47,8 @@ template <int S> struct P1Cfg { static constexpr int kThreads = (S <= 3) ? 768 :
 // every chunk stays 16-byte aligned for the 128-bit flush copies.
 __device__ __forceinline__ uint32_t stage_slot(uint32_t bucket, uint32_t pos) { return bucket * kStageCap + pos; }
 
-__host__ __device__ inline uint64_t flags_offset(int d) { return ((1ull << (2 * d)) - 4ull) / 3ull; }
+// sum_{e<d} 4^e = (4^d - 4) / 3; (4^d - 1) / 3 is the bit pattern 0101..01 (d ones): no division on the event path
+__host__ __device__ inline uint64_t flags_offset(int d) { return (0x5555555555555555ull & ((1ull << (2 * d)) - 1ull)) - 1ull; }
 
 __device__ __forceinline__ uint4 ldg128(const uint8_t *p)
 {
@@ -87,7 +88,13 @@ __device__ __forceinline__ uint32_t zero_bytes_nibble(uint32_t u)
     uint32_t f = (nz ^ 0x80808080u) >> 7;                                  // bit 0 of every zero byte
     return (f * 0x08040201u) >> 24;                                        // byte0->bit3 ... byte3->bit0
 }
-__device__ __forceinline__ uint32_t count_bytes_equal(uint32_t w, uint32_t splat) { return __popc(zero_bytes_nibble(w ^ splat)); }
+__device__ __forceinline__ uint32_t count_n_or_gt(uint32_t w)
+{
+    uint32_t u = w ^ 0x4E4E4E4Eu;            // 'N' -> 0x00, '>' -> 0x70
+    u ^= (u & 0x10101010u) * 7u;             // 0x70 -> 0x00; no other byte value becomes zero
+    const uint32_t nz = (((u & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | u) & 0x80808080u;
+    return 4u - __popc(nz);
+}
 
 struct Group {
     uint32_t code;   // 16 bases x 2 bits, first byte in bits 31..30
@@ -107,10 +114,8 @@ __device__ __forceinline__ Group pack_group(const uint4 &g, uint32_t &unknown)
     r.valid = 0xFFFFu;
     if ((b0 | b1 | b2 | b3) != 0) {  // rare in sequence data: some byte is not a base
         r.valid = (zero_bytes_nibble(b0) << 12) | (zero_bytes_nibble(b1) << 8) | (zero_bytes_nibble(b2) << 4) | zero_bytes_nibble(b3);
-        uint32_t nN = count_bytes_equal(g.x, 0x4E4E4E4Eu) + count_bytes_equal(g.y, 0x4E4E4E4Eu) + count_bytes_equal(g.z, 0x4E4E4E4Eu) +
-                      count_bytes_equal(g.w, 0x4E4E4E4Eu);
-        uint32_t nH = count_bytes_equal(g.x, 0x3E3E3E3Eu) + count_bytes_equal(g.y, 0x3E3E3E3Eu) + count_bytes_equal(g.z, 0x3E3E3E3Eu) +
-                      count_bytes_equal(g.w, 0x3E3E3E3Eu);
+        // bytes that are 'N' (0x4E) or '>' (0x3E) reset silently; both map to a zero byte under u -> u ^ 7*(u & 0x10), u = w ^ 'N'
+        uint32_t nN = count_n_or_gt(g.x) + count_n_or_gt(g.y) + count_n_or_gt(g.z) + count_n_or_gt(g.w), nH = 0;
         unknown += 16 - __popc(r.valid) - nN - nH;
     }
     return r;
@@ -141,20 +146,25 @@ __device__ __noinline__ void red_kmers_of_word(uint32_t wcode, uint32_t *table_k
     for (int t = 0; t < S; ++t) red_add_u32(table_k + ((wcode >> (2 * (S - 1 - t))) & kmask), amount);
 }
 
-// rare per-run events of one group (positions given as bits of 16-bit masks, first byte = bit 15)
+// rare per-run events of one group (positions given as bits of 16-bit masks, first byte = bit 15).
+// ev[0..3] head_base, ev[4..7] short_first, ev[8] runs_ge_k: CTA-private counters in shared memory -- soft-masked /
+// N-rich genomes have millions of run boundaries, and global atomics on nine fixed addresses would serialise them.
 __device__ __noinline__ void group_events(uint32_t first_k, uint32_t shorts, uint32_t m32, uint32_t code_hi, uint32_t code_lo, int k,
-                                          uint8_t *flags, fkb_partials *P)
+                                          uint8_t *flags, uint32_t *ev)
 {
     const uint32_t kmask = (k == 16) ? 0xffffffffu : ((1u << (2 * k)) - 1u);
     while (first_k) {  // run length reached exactly k here: first k-1 bases of the window go to head_base (:1050-1056)
         int b = 31 - __clz(first_k);
         first_k &= ~(1u << b);
         uint32_t kmer = __funnelshift_r(code_lo, code_hi, 2 * b) & kmask;
-        uint32_t head = kmer >> 2, cnt[4] = {0, 0, 0, 0};
-        for (int i = 0; i < k - 1; ++i) { cnt[head & 3u]++; head >>= 2; }
-        for (int c = 0; c < 4; ++c)
-            if (cnt[c]) atomicAdd(&P->head_base[c], (unsigned long long)cnt[c]);
-        atomicAdd(&P->runs_ge_k, 1ull);
+        const uint32_t head = kmer >> 2;  // the first k-1 bases; composition by popcounts of the 2-bit digits
+        const uint32_t lo = head & 0x55555555u, hi = (head >> 1) & 0x55555555u;
+        const uint32_t cT = __popc(lo & hi), cG = __popc(hi & ~lo), cC = __popc(lo & ~hi), cA = (uint32_t)(k - 1) - cT - cG - cC;
+        if (cA) atomicAdd(&ev[0], cA);
+        if (cC) atomicAdd(&ev[1], cC);
+        if (cG) atomicAdd(&ev[2], cG);
+        if (cT) atomicAdd(&ev[3], cT);
+        atomicAdd(&ev[8], 1u);
     }
     while (shorts) {  // valid base whose run is still shorter than k: the reference inserts a short path (:1059-1062)
         int b = 31 - __clz(shorts);
@@ -162,7 +172,7 @@ __device__ __noinline__ void group_events(uint32_t first_k, uint32_t shorts, uin
         int run = __ffs(~(m32 >> b)) - 1;  // consecutive valid bytes ending here (1 .. k-1)
         uint32_t prefix = __funnelshift_r(code_lo, code_hi, 2 * b) & ((1u << (2 * run)) - 1u);
         flags[flags_offset(run) + prefix] = 1;
-        atomicAdd(&P->short_first[prefix >> (2 * (run - 1))], 1ull);
+        atomicAdd(&ev[4 + (prefix >> (2 * (run - 1)))], 1u);
     }
 }
 
@@ -183,6 +193,7 @@ struct P1Smem {
     uint16_t stage[kNB * kStageCap];
     uint32_t cursor[kNB];  // items staged in the row
     uint32_t goff[kNB];    // items already appended to this CTA's region of the bucket (multiple of 8 until the end)
+    uint32_t ev[16];       // per-run event counters (see group_events), flushed to the partials once per tile
 };
 
 // predicated shared-memory atomic / store on 32-bit shared addresses: no branches, so the 8 atomics of a batch issue
@@ -245,6 +256,7 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
     const uint32_t cursor_sa = (uint32_t)__cvta_generic_to_shared(sm.cursor), stage_sa = (uint32_t)__cvta_generic_to_shared(sm.stage);
 
     for (int b = threadIdx.x; b < kNB; b += kP1Threads) { sm.cursor[b] = 0; sm.goff[b] = 0; }
+    if (threadIdx.x < 16) sm.ev[threadIdx.x] = 0;
     __syncthreads();
 
     // this warp's contiguous share of the interior
@@ -308,7 +320,9 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
             const bool edge = (cbase == lo) || (cbase + CH == hi);
 
             uint32_t emit[S + 2];
-            const bool all_emit = (vall == 0xFFFFu && !edge);
+            // warp-uniform choice: if any lane needs the general path the whole warp takes it (it is correct for clean
+            // chunks too); a per-lane branch would execute both paths back to back on soft-masked / N-rich input
+            const bool all_emit = __all_sync(0xffffffffu, vall == 0xFFFFu && !edge);
             if (all_emit) {
                 // ---- fast path: 16*(S+2) valid bases around me: every anchored window exists, nothing is left over ----
 #pragma unroll
@@ -343,7 +357,7 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
                     if (m != 0xFFFFFFFFu) {
                         const uint32_t first_k = rk & ~(m >> K) & 0xFFFFu;
                         const uint32_t shorts = grp[g].valid & ~rk;
-                        if (first_k | shorts) group_events(first_k, shorts, m, grp[g - 1].code, grp[g].code, K, flags, P);
+                        if (first_k | shorts) group_events(first_k, shorts, m, grp[g - 1].code, grp[g].code, K, flags, sm.ev);
                     }
                 }
             }
@@ -403,6 +417,14 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
 
         // ---- flush: append whole 16-byte chunks of every staged row to this CTA's region of the bucket ----
         __syncthreads();
+        if (threadIdx.x < 9) {  // per-run event counters of this tile (32-bit in shared memory) -> 64-bit partials
+            const uint32_t v = sm.ev[threadIdx.x];
+            if (v) {
+                sm.ev[threadIdx.x] = 0;
+                unsigned long long *dst = threadIdx.x < 4 ? &P->head_base[threadIdx.x] : (threadIdx.x < 8 ? &P->short_first[threadIdx.x - 4] : &P->runs_ge_k);
+                atomicAdd(dst, (unsigned long long)v);
+            }
+        }
         {
             const uint32_t sub = lane >> 3, c = lane & 7;  // 4 buckets per warp step, 8 lanes each
             const uint64_t bstride = (uint64_t)gridDim.x * cap_cb;
@@ -525,26 +547,77 @@ count_buckets_kernel(const uint16_t *__restrict__ gbuf, uint32_t cap_cb, const u
 }
 
 // ------------------------------------------------------------------------------------------------
-// pass 3: fold T_W (16-bit) into T_k (32-bit).  Thread x gathers, for every offset t of the k-mer inside the
-// word, the 4^t prefixes a (strided) times the 4^(J-t) suffixes (contiguous).  Consecutive x are contiguous.
+// pass 3: fold T_W (16-bit W-mers at stride S) into T_k, one base per level.
+//   suf_m[y] = occurrences of y as the LAST m bases of a sampled window        suf_W = T_W,  suf_{m-1}[y] = sum_c suf_m[c y]
+//   all_m[y] = occurrences of y at ANY offset inside a sampled window          all_W = T_W,  all_{m-1}[y] = sum_b all_m[y b] + suf_{m-1}[y]
+// (an (m-1)-mer inside a window is either the prefix of an m-mer in it, or the window's last m-1 bases.)
+// all_k is the count of every k-mer covered by a sampled window: T_k += all_k.  Work: ~2 * 4^W reads, no atomics.
 // ------------------------------------------------------------------------------------------------
-template <int S>
-__global__ void __launch_bounds__(256) fold_kernel(const uint16_t *__restrict__ table_w, uint32_t *__restrict__ table_k)
+template <typename TIn>
+__global__ void __launch_bounds__(256) fold_level_kernel(const TIn *__restrict__ all_in, const TIn *__restrict__ suf_in, int m,  // inputs are 4^m
+                                                         uint32_t *__restrict__ all_out, uint32_t *__restrict__ suf_out,
+                                                         uint32_t *__restrict__ table_k /* last level: add instead of store */)
 {
-    constexpr int J = S - 1, K = kW - S + 1;
-    const uint64_t n = 1ull << (2 * K);
-    for (uint64_t x = (uint64_t)blockIdx.x * 256 + threadIdx.x; x < n; x += (uint64_t)gridDim.x * 256) {
-        uint32_t sum = 0;
-#pragma unroll
-        for (int t = 0; t <= J; ++t) {
-            const int suf = J - t;                        // bases after the k-mer
-            const uint64_t mid = x << (2 * suf);
-            for (uint32_t a = 0; a < (1u << (2 * t)); ++a) {
-                const uint16_t *p = table_w + (((uint64_t)a << (2 * (kW - t))) | mid);
-                for (uint32_t b = 0; b < (1u << (2 * suf)); ++b) sum += p[b];
-            }
+    const uint64_t n = 1ull << (2 * (m - 1));
+    for (uint64_t y = (uint64_t)blockIdx.x * 256 + threadIdx.x; y < n; y += (uint64_t)gridDim.x * 256) {
+        const uint32_t suf = (uint32_t)suf_in[y] + suf_in[n + y] + suf_in[2 * n + y] + suf_in[3 * n + y];
+        uint32_t all;
+        if constexpr (sizeof(TIn) == 2) {
+            const uint2 v = *reinterpret_cast<const uint2 *>(all_in + 4 * y);  // four consecutive 16-bit entries
+            all = (v.x & 0xFFFFu) + (v.x >> 16) + (v.y & 0xFFFFu) + (v.y >> 16);
+        } else {
+            const uint4 v = *reinterpret_cast<const uint4 *>(all_in + 4 * y);
+            all = v.x + v.y + v.z + v.w;
         }
-        if (sum) table_k[x] += sum;
+        all += suf;
+        if (table_k) {
+            if (all) table_k[y] += all;
+        } else {
+            all_out[y] = all;
+            suf_out[y] = suf;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) fold_copy_kernel(const uint16_t *__restrict__ table_w, uint32_t *__restrict__ table_k, uint64_t n)
+{
+    for (uint64_t x = (uint64_t)blockIdx.x * 256 + threadIdx.x; x < n; x += (uint64_t)gridDim.x * 256) {
+        const uint32_t v = table_w[x];
+        if (v) table_k[x] += v;
+    }
+}
+
+// scratch: for every level m-1 in [k .. W-1) an `all` and a `suf` array of 4^(m-1) uint32
+inline uint32_t *fold_level_ptr(uint32_t *scratch, int level /* entries 4^level */, int which)
+{
+    uint64_t off = 0;
+    for (int l = kW - 1; l > level; --l) off += 2ull << (2 * l);
+    return scratch + off + (which ? (1ull << (2 * level)) : 0);
+}
+
+template <int S>
+cudaError_t run_fold(const LaunchInfo &li, const BucketScratch &bs, uint32_t *d_table, cudaStream_t st, int *launches)
+{
+    constexpr int K = kW - S + 1;
+    const uint64_t cap = (uint64_t)li.sm_count * 8;
+    auto grid = [&](uint64_t n) { uint64_t b = (n + 255) / 256; return (unsigned)(b < cap ? (b ? b : 1) : cap); };
+    if constexpr (S == 1) {
+        fold_copy_kernel<<<grid(1ull << (2 * kW)), 256, 0, st>>>(bs.table_w, d_table, 1ull << (2 * kW));
+        if (launches) ++*launches;
+        return cudaGetLastError();
+    } else {
+    for (int m = kW; m > K; --m) {  // 4^m -> 4^(m-1)
+        const bool last = (m - 1 == K);
+        uint32_t *all_out = last ? nullptr : fold_level_ptr(bs.fold, m - 1, 0), *suf_out = last ? nullptr : fold_level_ptr(bs.fold, m - 1, 1);
+        const uint64_t n = 1ull << (2 * (m - 1));
+        if (m == kW)
+            fold_level_kernel<uint16_t><<<grid(n), 256, 0, st>>>(bs.table_w, bs.table_w, m, all_out, suf_out, last ? d_table : nullptr);
+        else
+            fold_level_kernel<uint32_t><<<grid(n), 256, 0, st>>>(fold_level_ptr(bs.fold, m, 0), fold_level_ptr(bs.fold, m, 1), m, all_out, suf_out,
+                                                                 last ? d_table : nullptr);
+        if (launches) ++*launches;
+    }
+    return cudaGetLastError();
     }
 }
 
@@ -566,12 +639,10 @@ cudaError_t run_bucketed(const LaunchInfo &li, const BucketScratch &bs, const ui
     if (e != cudaSuccess) return e;
     bucketize_kernel<S><<<bs.n_cta, P1Cfg<S>::kThreads, sizeof(P1Smem), st>>>(d_stream, lo, n_witers, bs.gbuf, bs.cap_cb, bs.gcount, d_table, d_flags, d_partials);
     count_buckets_kernel<S><<<li.sm_count, kP2Threads, 128 * 1024, st>>>(bs.gbuf, bs.cap_cb, bs.gcount, bs.n_cta, bs.table_w, d_table, bs.work);
-    constexpr int K = kW - S + 1;
-    const uint64_t n = 1ull << (2 * K);
-    uint64_t fb = (n + 255) / 256, cap = (uint64_t)li.sm_count * 8;
-    fold_kernel<S><<<(int)(fb < cap ? fb : cap), 256, 0, st>>>(bs.table_w, d_table);
-    if (launches) *launches += 3;
-    return cudaGetLastError();
+    if (launches) *launches += 2;
+    cudaError_t e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) return e2;
+    return run_fold<S>(li, bs, d_table, st, launches);
 }
 
 }  // namespace
@@ -585,6 +656,12 @@ uint64_t bucket_unit_bytes(int k)
 }
 
 size_t bucket_table_w_bytes() { return ((size_t)1 << (2 * kW)) * sizeof(uint16_t); }
+size_t bucket_fold_bytes()
+{
+    size_t words = 0;
+    for (int l = kW - 1; l >= 6; --l) words += (size_t)2 << (2 * l);
+    return words * sizeof(uint32_t);
+}
 int bucket_count() { return kNB; }
 
 cudaError_t launch_count_bucketed(const LaunchInfo &li, const BucketScratch &bs, const uint8_t *d_stream, uint64_t lo, uint64_t hi, int k,

@@ -22,7 +22,8 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kChunk = 64;  // bytes owned per thread per iteration
 
-__host__ __device__ inline uint64_t flags_offset(int d) { return ((1ull << (2 * d)) - 4ull) / 3ull; }  // sum_{e<d} 4^e
+// sum_{e<d} 4^e = (4^d - 4) / 3; (4^d - 1) / 3 is the bit pattern 0101..01 (d ones): no division on the event path
+__host__ __device__ inline uint64_t flags_offset(int d) { return (0x5555555555555555ull & ((1ull << (2 * d)) - 1ull)) - 1ull; }  // sum_{e<d} 4^e
 
 // 128-bit read-only load.  The stream is read once; neighbouring lanes share 32-byte sectors across the
 // five loads of an iteration, so L1 allocation is kept (no .no_allocate).
@@ -90,28 +91,29 @@ struct Tally {
 //             base is recovered from the table at finalize, the first k-1 go to head_base here.
 //  run <  k : the reference inserts the run so far as a short path (:1059-1062) => a depth-`run` trie node;
 //             recorded as a prefix flag, and as a visit of the depth-1 node of the run's first base.
-__device__ __noinline__ void rare_event(uint32_t kmer, int run, int k, uint8_t *flags, fkb_partials *P)
+// ev[0..3] head_base, ev[4..7] short_first, ev[8] runs_ge_k: CTA-private shared-memory counters (run boundaries are
+// frequent in soft-masked / N-rich genomes; global atomics on nine fixed addresses would serialise them).
+__device__ __noinline__ void rare_event(uint32_t kmer, int run, int k, uint8_t *flags, uint32_t *ev)
 {
     if (run == k) {
-        uint32_t head = kmer >> 2;
-        uint32_t cnt[4] = {0, 0, 0, 0};
-        for (int i = 0; i < k - 1; ++i) {
-            cnt[head & 3u]++;
-            head >>= 2;
-        }
-        for (int b = 0; b < 4; ++b)
-            if (cnt[b]) atomicAdd(&P->head_base[b], (unsigned long long)cnt[b]);
-        atomicAdd(&P->runs_ge_k, 1ull);
+        const uint32_t head = kmer >> 2;  // the first k-1 bases; composition by popcounts of the 2-bit digits
+        const uint32_t lo = head & 0x55555555u, hi = (head >> 1) & 0x55555555u;
+        const uint32_t cT = __popc(lo & hi), cG = __popc(hi & ~lo), cC = __popc(lo & ~hi), cA = (uint32_t)(k - 1) - cT - cG - cC;
+        if (cA) atomicAdd(&ev[0], cA);
+        if (cC) atomicAdd(&ev[1], cC);
+        if (cG) atomicAdd(&ev[2], cG);
+        if (cT) atomicAdd(&ev[3], cT);
+        atomicAdd(&ev[8], 1u);
     } else {  // 1 <= run < k
         uint32_t prefix = kmer & ((1u << (2 * run)) - 1u);
         flags[flags_offset(run) + prefix] = 1;
-        atomicAdd(&P->short_first[prefix >> (2 * (run - 1))], 1ull);
+        atomicAdd(&ev[4 + (prefix >> (2 * (run - 1)))], 1u);
     }
 }
 
 template <bool EDGE>
 __device__ __forceinline__ void step_owned(Scan &s, uint32_t c, uint32_t mask, int k, uint32_t *table, uint8_t *flags,
-                                           fkb_partials *P, Tally &t, uint64_t pos, uint64_t begin, uint64_t end)
+                                           uint32_t *P, Tally &t, uint64_t pos, uint64_t begin, uint64_t end)
 {
     uint32_t code = base_code(c);
     bool valid = base_valid(c, code);
@@ -131,7 +133,7 @@ __device__ __forceinline__ void step_owned(Scan &s, uint32_t c, uint32_t mask, i
 
 template <bool EDGE>
 __device__ __forceinline__ void scan_word(Scan &s, uint32_t w, uint32_t mask, int k, uint32_t *table, uint8_t *flags,
-                                          fkb_partials *P, Tally &t, uint64_t pos, uint64_t begin, uint64_t end)
+                                          uint32_t *P, Tally &t, uint64_t pos, uint64_t begin, uint64_t end)
 {
 #pragma unroll
     for (int j = 0; j < 4; ++j) step_owned<EDGE>(s, (w >> (8 * j)) & 0xffu, mask, k, table, flags, P, t, pos + j, begin, end);
@@ -148,6 +150,9 @@ __global__ void __launch_bounds__(kThreads) count_direct_kernel(const uint8_t *_
 {
     if (blockIdx.y == 1) { begin = begin2; end = end2; }
     if (end <= begin) return;
+    __shared__ uint32_t ev[16];
+    if (threadIdx.x < 16) ev[threadIdx.x] = 0;
+    __syncthreads();
     const uint32_t mask = (k == 16) ? 0xffffffffu : ((1u << (2 * k)) - 1u);
     const uint64_t base = begin & ~15ull;                      // chunks are 16-byte aligned in the stream
     const uint64_t n_chunks = (end - base + kChunk - 1) / kChunk;
@@ -167,7 +172,7 @@ __global__ void __launch_bounds__(kThreads) count_direct_kernel(const uint8_t *_
                 for (int j = 0; j < 4; ++j) step_context(sc, (hw[i] >> (8 * j)) & 0xffu, mask);
             const uint32_t w[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
 #pragma unroll
-            for (int i = 0; i < 16; ++i) scan_word<false>(sc, w[i], mask, k, table, flags, P, t, p0 + 4 * i, begin, end);
+            for (int i = 0; i < 16; ++i) scan_word<false>(sc, w[i], mask, k, table, flags, ev, t, p0 + 4 * i, begin, end);
         } else {
             uint4 h = load16_guarded(s, (int64_t)p0 - 16, end);
             const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
@@ -176,9 +181,14 @@ __global__ void __launch_bounds__(kThreads) count_direct_kernel(const uint8_t *_
             for (int g = 0; g < 4; ++g) {
                 uint4 v = load16_guarded(s, (int64_t)(p0 + 16 * g), end);
                 const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                for (int i = 0; i < 4; ++i) scan_word<true>(sc, w[i], mask, k, table, flags, P, t, p0 + 16 * g + 4 * i, begin, end);
+                for (int i = 0; i < 4; ++i) scan_word<true>(sc, w[i], mask, k, table, flags, ev, t, p0 + 16 * g + 4 * i, begin, end);
             }
         }
+    }
+    __syncthreads();
+    if (threadIdx.x < 9 && ev[threadIdx.x]) {
+        unsigned long long *dst = threadIdx.x < 4 ? &P->head_base[threadIdx.x] : (threadIdx.x < 8 ? &P->short_first[threadIdx.x - 4] : &P->runs_ge_k);
+        atomicAdd(dst, (unsigned long long)ev[threadIdx.x]);
     }
     unsigned long long win = warp_sum(t.windows), unk = warp_sum(t.unknown), val = warp_sum(t.valid);
     if ((threadIdx.x & 31) == 0) {

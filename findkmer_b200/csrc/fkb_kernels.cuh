@@ -21,6 +21,7 @@ struct BucketScratch {
     uint32_t *gcount = nullptr;    // [n_buckets][n_cta] items in each segment
     uint32_t *work = nullptr;      // pass-2 work counter
     uint16_t *table_w = nullptr;   // [4^W] 16-bit W-mer counts
+    uint32_t *fold = nullptr;      // per-level (all, suf) arrays of the fold
 };
 
 struct LaunchInfo {
@@ -32,6 +33,7 @@ struct LaunchInfo {
 int bucket_stride_for(int k);        // S = W - k + 1 when the bucketed path supports k, else 0
 uint64_t bucket_unit_bytes(int k);   // interior granularity of the bucketed path
 size_t bucket_table_w_bytes();
+size_t bucket_fold_bytes();
 int bucket_count();
 cudaError_t launch_count_bucketed(const LaunchInfo &li, const BucketScratch &bs, const uint8_t *d_stream, uint64_t lo, uint64_t hi, int k,
                                   uint32_t *d_table, uint8_t *d_flags, fkb_partials *d_partials, cudaStream_t st, int *launches);

@@ -386,3 +386,44 @@ def test_full_size_properties(counter):
     assert (split.n_kmers, split.base_count, split.node_count) == (whole.n_kmers, whole.base_count, whole.node_count)
     del d
     torch.cuda.empty_cache()
+
+
+# ---- the drop-in program against the untouched reference binary ---------------------------------------------
+def test_cli_binary_is_a_drop_in(harness, tmp_path):
+    """findkmer_b200/bin/findKmer vs oracle/_ref/findKmer: same flags, same output file names, identical bytes"""
+    import subprocess
+    from conftest import ROOT
+    from findkmer_b200 import synth
+    exe = ROOT / "findkmer_b200" / "bin" / "findKmer"
+    if not exe.exists() or not harness.reference_available():
+        pytest.skip("CLI or reference binary not built")
+    data = synth.render(synth.config5(n_bases=700_000))
+    for k, z, export in ((6, None, None), (8, 2, None), (11, None, "mine.csv")):
+        ref = harness.run_reference(data, k, z=z, name="genome.fa", export=export)
+        work = tmp_path / f"cli_{k}"
+        work.mkdir()
+        data.tofile(work / "genome.fa")
+        argv = [str(exe), "-q", "1", "-k", str(k), "-p", "genome.fa"]
+        if z is not None:
+            argv += ["-z", str(z)]
+        if export:
+            argv += ["-e", export]
+        run = subprocess.run(argv, cwd=work, capture_output=True, text=True, timeout=300)
+        assert run.returncode == 0, run.stderr[-500:]
+        assert (work / ref.csv_name).read_bytes() == ref.csv
+        assert (work / ref.stats_name).read_bytes() == ref.stats
+        # the stdout lines scripts may grep (the reference prints them too)
+        for phrase in ("ATTEMPTING CONFIGURATION", "!!!Find The KMER!!!", "Reading sequence from file", "Statistics of occurrences",
+                       "valid bases total INSIDE sequences >= k.", "tree density.", "Now creating histogram.", "histogram creation finished."):
+            assert phrase in run.stdout and phrase in ref.stdout, phrase
+        line = [ln for ln in ref.stdout.split("\n") if "tree density" in ln][0]
+        assert line in run.stdout
+    # error behaviour: empty file -> message + exit 1, header-only CSV left behind (as the reference does)
+    work = tmp_path / "cli_empty"
+    work.mkdir()
+    (work / "empty.fa").write_bytes(b"")
+    run = subprocess.run([str(exe), "-q", "1", "-k", "7", "-p", "empty.fa"], cwd=work, capture_output=True, text=True, timeout=120)
+    assert run.returncode == 1 and "Sequence File Is Empty" in run.stderr
+    assert (work / "7mer_Historam_Of_empty.fa.csv").read_bytes() == b"Sequence, Shannon Entropy h, Shannon Entropy H, Frequency, Z score"
+    run = subprocess.run([str(exe), "-h"], cwd=work, capture_output=True, text=True, timeout=60)
+    assert run.returncode == 1 and "Usage: findKmer [options]" in run.stdout
