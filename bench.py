@@ -219,7 +219,7 @@ def main():
         torch.cuda.synchronize()
 
     def reduce_acc():
-        reduce_accumulators(acc.table, acc.flags, acc.partials, dst=0)
+        reduce_accumulators(acc.table, acc.flags, acc.partials, dst=0, fused=acc.buf)
 
     ev_pairs = []
 

@@ -77,7 +77,8 @@ def load() -> ctypes.CDLL:
     if not LIB_PATH.exists():
         from . import build as _build
         _build.build()
-    lib = ctypes.CDLL(str(LIB_PATH))
+    import os
+    lib = ctypes.CDLL(os.environ.get("FKB_LIB", str(LIB_PATH)))  # FKB_LIB: a tuning variant built by build.build_variant()
     ctx = c_void_p
     lib.fkb_create.argtypes = [c_int, POINTER(ctx)]
     lib.fkb_create.restype = c_int

@@ -73,6 +73,22 @@ def build(verbose: bool = False, force: bool = False) -> Path:
     return LIB
 
 
+def build_variant(name: str, defines, verbose: bool = False) -> Path:
+    """A tuning variant of the library (profiling only): same sources, extra -D flags, written to build/variants/."""
+    vdir = ROOT / "build" / "variants" / name
+    vdir.mkdir(parents=True, exist_ok=True)
+    objs = []
+    for src in CU_SOURCES:
+        o = vdir / (src + ".o")
+        _run([NVCC] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-c", CSRC / src, "-o", o], verbose)
+        objs.append(o)
+    for src in CXX_SOURCES:
+        objs.append(OBJ / (src + ".o"))
+    out = PKG / f"libfindkmer_b200_{name}.so"
+    _run([NVCC] + ARCH + ["-shared", "-o", out] + objs + ["-lpthread"], verbose)
+    return out
+
+
 if __name__ == "__main__":
     build(verbose=True, force="--force" in sys.argv)
     print(LIB)

@@ -36,11 +36,23 @@ constexpr int kW = 13;                       // counted word length
 constexpr int kBucketBits = 2 * kW - 16;     // 10
 constexpr int kNB = 1 << kBucketBits;        // 1024 buckets
 constexpr int kStageCap = 104;               // staged items per bucket (13 chunks of 8): 1024 rows of 208 B = 208 KiB
-constexpr int kTileItems = 64 * kNB;         // items a CTA stages between flushes: ~64 per bucket on average (+ <= 7 carried) of 104
-constexpr int kP2Threads = 1024;
+#ifndef FKB_TILE_AVG
+#define FKB_TILE_AVG 64
+#endif
+#ifndef FKB_P1_THREADS_LO
+#define FKB_P1_THREADS_LO 512  // measured: 512 > 640 > 768 > 1024 at S = 3 (registers beat warps: 80-register builds spill)
+#endif
+#ifndef FKB_P1_THREADS_HI
+#define FKB_P1_THREADS_HI 448  // measured best at S = 6
+#endif
+#ifndef FKB_P2_THREADS
+#define FKB_P2_THREADS 1024
+#endif
+constexpr int kTileItems = FKB_TILE_AVG * kNB;         // items a CTA stages between flushes: ~64 per bucket on average (+ <= 7 carried) of 104
+constexpr int kP2Threads = FKB_P2_THREADS;
 
-// pass-1 CTA size: as many warps as the register budget of the stride allows (1 CTA per SM: the staging rows take 192 KiB)
-template <int S> struct P1Cfg { static constexpr int kThreads = (S <= 3) ? 768 : 512; };
+// pass-1 CTA size (1 CTA per SM: the staging rows take 208 KiB), tuned on B200 with build.build_variant()
+template <int S> struct P1Cfg { static constexpr int kThreads = (S <= 3) ? FKB_P1_THREADS_LO : FKB_P1_THREADS_HI; };
 
 // Staging rows are 208 bytes (13 chunks of 16 bytes) apart: 52 words == 20 banks, so consecutive rows start on 8
 // different bank offsets and a warp's stores (all rows fill at about the same rate) spread over all 32 banks, while
@@ -435,6 +447,7 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
                 uint16_t *dst = my_gbuf + b * bstride + off;
                 uint4 tail = make_uint4(0, 0, 0, 0);
                 const bool has_tail = (c == 0) && n8 && cnt > n8;
+                uint32_t esc = 0;
                 if (has_tail) tail = *reinterpret_cast<const uint4 *>(row + n8);  // the <= 7 items that stay staged
 #pragma unroll
                 for (int cc = 0; cc < 2; ++cc) {
@@ -442,8 +455,12 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
                     if (i0 < n8) {
                         const uint4 v = *reinterpret_cast<const uint4 *>(row + i0);
                         if (off + i0 + 8 <= cap_cb) *reinterpret_cast<uint4 *>(dst + i0) = v;
-                        else escape_chunk<S>(b, v, table_k);  // this CTA's region of the bucket is full (heavily skewed input)
+                        else esc |= 1u << cc;
                     }
+                }
+                if (esc) {  // this CTA's region of the bucket is full (heavily skewed input): exact escape, off the copy loop
+                    for (int cc = 0; cc < 2; ++cc)
+                        if (esc & (1u << cc)) escape_chunk<S>(b, *reinterpret_cast<const uint4 *>(row + (c + 8 * cc) * 8u), table_k);
                 }
                 __syncwarp();
                 if (c == 0) {

@@ -255,6 +255,29 @@ __global__ void __launch_bounds__(kThreads) finalize_depth_kernel(uint8_t *__res
     if ((threadIdx.x & 31) == 0 && nodes) atomicAdd(&scratch[9], nodes);
 }
 
+// all trie depths d_top .. 1 in ONE block (4^8 = 65536 flags at most): the levels are tiny and strictly sequential
+__global__ void __launch_bounds__(1024) finalize_low_depths_kernel(uint8_t *__restrict__ flags, int d_top, unsigned long long *__restrict__ scratch)
+{
+    __shared__ unsigned long long s_nodes;
+    if (threadIdx.x == 0) s_nodes = 0;
+    __syncthreads();
+    unsigned long long nodes = 0;
+    for (int d = d_top; d >= 1; --d) {
+        const uint32_t groups = 1u << (2 * (d - 1));
+        const uint32_t *lvl = reinterpret_cast<const uint32_t *>(flags + flags_offset(d));
+        for (uint32_t g = threadIdx.x; g < groups; g += 1024) {
+            const uint32_t v = lvl[g];
+            nodes += ((v & 0xffu) != 0) + ((v & 0xff00u) != 0) + ((v & 0xff0000u) != 0) + ((v & 0xff000000u) != 0);
+            if (d > 1 && v != 0) flags[flags_offset(d - 1) + g] = 1;
+        }
+        __syncthreads();  // level d-1 is complete before it is read
+    }
+    nodes = warp_sum(nodes);
+    if ((threadIdx.x & 31) == 0 && nodes) atomicAdd(&s_nodes, nodes);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_nodes) atomicAdd(&scratch[9], s_nodes);
+}
+
 __global__ void finalize_counts_kernel(const unsigned long long *__restrict__ scratch, const fkb_partials *__restrict__ P,
                                        uint64_t stream_bytes, fkb_counts *__restrict__ out)
 {
@@ -418,8 +441,13 @@ cudaError_t launch_finalize(const LaunchInfo &li, int k, const uint32_t *d_table
     if (e != cudaSuccess) return e;
     finalize_table_kernel<<<grid_for(1ull << (2 * (k - 1)), li.sm_count, 8), kThreads, 0, st>>>(d_table, k, d_flags, d_scratch);
     if (launches) ++*launches;
-    for (int d = k - 1; d >= 1; --d) {
+    int d = k - 1;
+    for (; d > 8; --d) {  // wide levels: one launch each
         finalize_depth_kernel<<<grid_for(1ull << (2 * (d - 1)), li.sm_count, 8), kThreads, 0, st>>>(d_flags, d, d_scratch);
+        if (launches) ++*launches;
+    }
+    if (d >= 1) {  // the remaining <= 8 levels in one block
+        finalize_low_depths_kernel<<<1, 1024, 0, st>>>(d_flags, d, d_scratch);
         if (launches) ++*launches;
     }
     finalize_counts_kernel<<<1, 32, 0, st>>>(d_scratch, d_partials, stream_bytes, d_counts);

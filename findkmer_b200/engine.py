@@ -65,19 +65,22 @@ def _host_view(data):
 
 class DeviceAccumulators:
     """Per-GPU accumulators of one counting job: table, short-run prefix flags, scalar partials.
-    All three combine across shards with one reduce each (sum, max, sum)."""
+    Table and flags share ONE int32 buffer so that a multi-GPU run combines them with a single sum-reduce
+    (a flag byte is 0/1 per rank, so byte-wise sums cannot carry for up to 255 ranks and "present" == non-zero);
+    the 12 partial scalars are a second, tiny sum-reduce."""
 
     def __init__(self, k: int, device):
         import torch
         lib = _lib.load()
         self.k = k
-        self.table = torch.zeros(lib.fkb_table_entries(k), dtype=torch.int32, device=device)   # uint32 bit patterns
-        self.flags = torch.zeros(lib.fkb_prefix_flags_bytes(k), dtype=torch.uint8, device=device)
+        n_table, n_flags = lib.fkb_table_entries(k), lib.fkb_prefix_flags_bytes(k)
+        self.buf = torch.zeros(n_table + (n_flags + 3) // 4, dtype=torch.int32, device=device)
+        self.table = self.buf[:n_table]                                   # uint32 bit patterns
+        self.flags = self.buf[n_table:].view(torch.uint8)[:n_flags]
         self.partials = torch.zeros(ctypes.sizeof(FkbPartials) // 8, dtype=torch.int64, device=device)
 
     def zero_(self):
-        self.table.zero_()
-        self.flags.zero_()
+        self.buf.zero_()
         self.partials.zero_()
 
 

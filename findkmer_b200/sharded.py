@@ -24,13 +24,18 @@ def shard_range(total: int, world: int, rank: int):
     return b, e, max(0, b - HALO)
 
 
-def reduce_accumulators(table, flags, partials, dst: int = 0, group=None):
-    """The one exchange step.  Tensors may live on CUDA (NCCL) or on the CPU (gloo, tests)."""
+def reduce_accumulators(table, flags, partials, dst: int = 0, group=None, fused=None):
+    """The one exchange step.  Tensors may live on CUDA (NCCL) or on the CPU (gloo, tests).
+    `fused`: an int32 tensor that holds table and flags back to back (DeviceAccumulators.buf) -- one collective
+    instead of two; flag bytes are 0/1 per rank, so their byte-wise sum is exact and "present" == non-zero."""
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
-    dist.reduce(table, dst, op=dist.ReduceOp.SUM, group=group)      # uint32 bit patterns in int32: wrap-around sums are exact
-    dist.reduce(flags, dst, op=dist.ReduceOp.MAX, group=group)      # presence bytes: OR == max
+    if fused is not None:
+        dist.reduce(fused, dst, op=dist.ReduceOp.SUM, group=group)
+    else:
+        dist.reduce(table, dst, op=dist.ReduceOp.SUM, group=group)  # uint32 bit patterns in int32: wrap-around sums are exact
+        dist.reduce(flags, dst, op=dist.ReduceOp.MAX, group=group)  # presence bytes: OR == max
     dist.reduce(partials, dst, op=dist.ReduceOp.SUM, group=group)
 
 

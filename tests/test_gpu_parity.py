@@ -141,8 +141,7 @@ def test_device_ranges_compose(counter, harness):
     mid = n // 2 + 3
     _, acc0 = _device_count(counter, stream, k, 0, mid)
     _, acc1 = _device_count(counter, stream, k, mid, n)
-    acc0.table += acc1.table
-    acc0.flags = torch.maximum(acc0.flags, acc1.flags)
+    acc0.buf += acc1.buf            # what the fused NCCL sum-reduce does: table words and flag bytes together
     acc0.partials += acc1.partials
     assert_counts_equal(counter.finalize_device(acc0, n), harness.oracle_count_stream(stream, k))
 
@@ -199,7 +198,7 @@ def test_bucketed_variant_matches_oracle(bucketed, harness, k):
     want = harness.oracle_count_stream(stream, k)
     launches0 = bucketed.launches
     got, _ = _device_count(bucketed, stream, k)
-    assert bucketed.launches - launches0 >= 4 + k  # edges + 3 bucketed passes + finalize: the bucketed path really ran
+    assert bucketed.launches - launches0 >= 6  # edges + bucketize + count_buckets + fold level(s) + finalize: the bucketed path really ran
     assert_counts_equal(got, want)
     got, _ = _device_count(bucketed, stream, k, 12345, len(stream) - 777, pieces=3)  # unaligned sub-ranges, three launches
     sub = harness.oracle_count_stream(stream[:len(stream) - 777], k)
