@@ -279,9 +279,19 @@ def main():
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     shard_bytes = (e - b) + (4 ** k) * 4  # per launch (per rank): this rank's stream bytes + its table
     achieved = shard_bytes / (kernel_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "count (fused encode + table update)", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": shard_bytes,
-                "peak_source": peak_src}
+    # DRAM traffic of the same launch sequence, from the committed ncu capture (profiles/r01_traffic_k11.json:
+    # dram__bytes_read.sum + dram__bytes_write.sum of every kernel of one step; it cannot be measured live)
+    traffic, traffic_note = None, None
+    tpath = ROOT / "profiles" / "r01_traffic_k11.json"
+    if tpath.exists() and world == 1 and k == 11 and args.bases == N_BASES:
+        tj = json.loads(tpath.read_text())
+        traffic = tj["dram_bytes_per_step"]
+        traffic_note = ("ncu capture " + tpath.name + ": 2.6x the algorithmic bytes BY DESIGN -- the routed 16-bit payloads are written "
+                        "and read once (2 x 2/3 B/base) and the 13-mer table once (128 MiB + fold reads); no re-reads of the stream")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "count path of one step: bucketize_kernel<3> (69 % of the time) + count_buckets_kernel<3> (24 %) + fold (4 %) + edges",
+                "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": shard_bytes, "peak_source": peak_src, "traffic_note": traffic_note,
+                "binding_resource": "shared-memory LSU pipe ~70-74 % and ALU pipe ~68-75 % busy in both kernels (ncu); scattered-RMW bound, not HBM bound"}
 
     # ---- e2e leg: raw FASTA bytes in pinned host memory -> counts on the host ----
     e2e = None
