@@ -13,7 +13,8 @@
 // Deliberate differences (DESIGN.md "boundary"): exit status 0 on success (the reference always dies in an
 // invalid free() after closing its files, :1370-1371); a missing option value prints usage once and exits 1
 // instead of looping forever (:1302-1303); unknown characters are reported once with a count instead of one
-// stderr line each (:581-585); k = 17..20 is refused (dense 4^k tables); -g/--gpus is an extension.
+// stderr line each (:581-585); k = 17..20 is refused (dense 4^k tables); -K/--ksweep (several k in one run: the file is
+// uploaded and stripped once) and -g/--gpus are extensions.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -42,6 +43,7 @@ struct Config {
     int z_enable = -1;
     long double z_threshold = -1;
     int gpus = 1;
+    std::vector<int> sweep;  // -K/--ksweep a-b | a,b,c : several k in one run (extension; one upload, one strip)
 };
 
 void usage()
@@ -123,6 +125,22 @@ bool parse_arguments(int argc, char **argv, Config &cfg)
             }
             cfg.z_enable = 1;
             cfg.z_threshold = atoi(argv[i]);
+        } else if (!strcmp(a, "-K") || !strcmp(a, "--ksweep")) {  // extension: the launcher's k loop in one process
+            if (++i == argc) { fprintf(stderr, "k sweep is missing. Usage is \"-K 6-11\" or \"-K 6,8,11\".\n"); return false; }
+            const char *p = argv[i];
+            int lo = atoi(p);
+            const char *dash = strchr(p, '-');
+            if (dash) {
+                int hi = atoi(dash + 1);
+                for (int k = lo; k <= hi; ++k) cfg.sweep.push_back(k);
+            } else {
+                for (const char *q = p; q && *q; q = strchr(q, ',') ? strchr(q, ',') + 1 : nullptr) cfg.sweep.push_back(atoi(q));
+            }
+            for (int k : cfg.sweep)
+                if (k < 1 || k > FKB_MAX_K) {
+                    fprintf(stderr, "%d is not a valid value for k.\nPlease select a number greater than zero and less than %d\n", k, FKB_MAX_K + 1);
+                    exit(EXIT_FAILURE);
+                }
         } else if (!strcmp(a, "-g") || !strcmp(a, "--gpus")) {  // extension
             if (++i == argc) { fprintf(stderr, "Number of GPUs is missing.\n"); return false; }
             cfg.gpus = atoi(argv[i]) > 0 ? atoi(argv[i]) : 1;
@@ -183,6 +201,7 @@ int main(int argc, char **argv)
 
     // print_conf, :307-364
     fprintf(stdout, "\nATTEMPTING CONFIGURATION: \n");
+    if (!cfg.sweep.empty()) cfg.k = cfg.sweep[0];  // the file opened below is then the first k's file, not a stray one
     finish_config(cfg);
     fprintf(stdout, "- sequence_file file: %s\n", cfg.sequence_file.c_str());
     fprintf(stdout, "- export file: %s\n", cfg.out_file.c_str());
@@ -233,16 +252,22 @@ int main(int argc, char **argv)
         fclose(csv);
         return EXIT_FAILURE;
     }
-    std::vector<uint32_t> table;
+    std::vector<int> ks = cfg.sweep.empty() ? std::vector<int>{cfg.k} : cfg.sweep;
+    std::vector<std::vector<uint32_t>> tables(ks.size());
+    std::vector<uint32_t *> table_ptrs(ks.size());
+    std::vector<fkb_counts> all_counts(ks.size());
     try {
-        table.resize(fkb_table_entries(cfg.k));
+        for (size_t i = 0; i < ks.size(); ++i) {
+            tables[i].resize(fkb_table_entries(ks[i]));
+            table_ptrs[i] = tables[i].data();
+        }
     } catch (...) {
         fprintf(stderr, "allocate_array():: memory allocation failed\n");
         return EXIT_FAILURE;
     }
-    fkb_counts counts;
-    memset(&counts, 0, sizeof counts);
-    status = fkb_count_file(ctx, cfg.sequence_file.c_str(), cfg.k, table.data(), &counts);
+    memset(all_counts.data(), 0, sizeof(fkb_counts) * ks.size());
+    if (ks.size() == 1) status = fkb_count_file(ctx, cfg.sequence_file.c_str(), ks[0], table_ptrs[0], &all_counts[0]);
+    else status = fkb_count_file_multi(ctx, cfg.sequence_file.c_str(), ks.data(), (int)ks.size(), table_ptrs.data(), all_counts.data());
     if (status == FKB_ERR_EMPTY_INPUT) {
         fprintf(stderr, "Sequence File Is Empty, Ending Program");  // :983
         fclose(csv);
@@ -263,45 +288,67 @@ int main(int argc, char **argv)
         fkb_destroy(ctx);
         return EXIT_FAILURE;
     }
-    if (counts.unknown_chars)
-        fprintf(stderr, "Unknown character processed! File may be corrupted. (%llu such characters; the reference prints one line each)\n",
-                (unsigned long long)counts.unknown_chars);
-
-    // ---- statistics(), :491-565 ----
-    const std::string stats_name = std::to_string(cfg.k) + "mer_Base_Stats_Of_" + cfg.sequence_file + ".txt";
-    FILE *stats = fopen(stats_name.c_str(), "w");
-    if (!stats) {
-        fprintf(stderr, "Out file failed to open\nFile MUST be in current directory.\n");
-        fclose(csv);
-        fkb_destroy(ctx);
-        return EXIT_FAILURE;
-    }
-    long double base_probability[4];
-    status = fkb_write_base_stats(stats, stdout, cfg.k, &counts, base_probability);
-    if (status == FKB_ERR_ZERO_BASE_PROBABILITY) {  // the reference exits with both files open; exit() flushes them
-        fclose(stats);
-        fclose(csv);
-        fkb_destroy(ctx);
-        return EXIT_FAILURE;
-    }
-    fclose(stats);
-
-    fprintf(stdout, "Now creating histogram.\n");
-    fflush(stdout);
-    uint64_t rows = 0;
-    status = fkb_write_histogram(csv, cfg.k, table.data(), &counts, base_probability, cfg.z_enable, cfg.z_threshold, 0, &rows);
-    if (status != FKB_OK) {
-        fprintf(stderr, "Out file write error! (%s)\n", fkb_status_string(status));
-        fclose(csv);
-        fkb_destroy(ctx);
-        return EXIT_FAILURE;
-    }
-    fprintf(stdout, "histogram creation finished.\n");
-    if (fclose(csv) == EOF)
-        fprintf(stderr, "Out file close error! This is not expected and might mean the data was not written to the file properly before the close.\n");
-    fprintf(stdout, "Your file can be found in the current directory as: \n    %s\n", cfg.out_file.c_str());
     fkb_destroy(ctx);
-    fprintf(stdout, "End of program was reached properly.\n\n");
+    if (all_counts[0].unknown_chars)
+        fprintf(stderr, "Unknown character processed! File may be corrupted. (%llu such characters; the reference prints one line each)\n",
+                (unsigned long long)all_counts[0].unknown_chars);
+
+    int exit_code = 0;
+    for (size_t i = 0; i < ks.size(); ++i) {
+        const int k = ks[i];
+        const fkb_counts &counts = all_counts[i];
+        std::string out_name = cfg.out_file;
+        if (ks.size() > 1) {  // sweep: every k gets the file names a separate run would have produced
+            Config one = cfg;
+            one.k = k;
+            one.have_out_file = false;
+            finish_config(one);
+            out_name = cfg.have_out_file ? std::to_string(k) + "mer_" + cfg.out_file : one.out_file;
+            if (i > 0 || out_name != cfg.out_file) {
+                if (i == 0) fclose(csv);
+                csv = fopen(out_name.c_str(), "w");
+                if (!csv) {
+                    fprintf(stderr, "Out file failed to open\nFile MUST be in current directory.\n");
+                    return EXIT_FAILURE;
+                }
+                fprintf(csv, OUT_FILE_COLUMN_HEADERS);
+            }
+            fprintf(stdout, "\n- k size: %d\n- export file: %s\n", k, out_name.c_str());
+        }
+        // ---- statistics(), :491-565 ----
+        const std::string stats_name = std::to_string(k) + "mer_Base_Stats_Of_" + cfg.sequence_file + ".txt";
+        FILE *stats = fopen(stats_name.c_str(), "w");
+        if (!stats) {
+            fprintf(stderr, "Out file failed to open\nFile MUST be in current directory.\n");
+            fclose(csv);
+            return EXIT_FAILURE;
+        }
+        long double base_probability[4];
+        status = fkb_write_base_stats(stats, stdout, k, &counts, base_probability);
+        fclose(stats);
+        if (status == FKB_ERR_ZERO_BASE_PROBABILITY) {  // the reference exits here with a header-only CSV
+            fclose(csv);
+            csv = nullptr;
+            exit_code = EXIT_FAILURE;
+            if (ks.size() == 1) return exit_code;
+            continue;
+        }
+        fprintf(stdout, "Now creating histogram.\n");
+        fflush(stdout);
+        uint64_t rows = 0;
+        status = fkb_write_histogram(csv, k, tables[i].data(), &counts, base_probability, cfg.z_enable, cfg.z_threshold, 0, &rows);
+        if (status != FKB_OK) {
+            fprintf(stderr, "Out file write error! (%s)\n", fkb_status_string(status));
+            fclose(csv);
+            return EXIT_FAILURE;
+        }
+        fprintf(stdout, "histogram creation finished.\n");
+        if (fclose(csv) == EOF)
+            fprintf(stderr, "Out file close error! This is not expected and might mean the data was not written to the file properly before the close.\n");
+        csv = nullptr;
+        fprintf(stdout, "Your file can be found in the current directory as: \n    %s\n", out_name.c_str());
+    }
+    if (exit_code == 0) fprintf(stdout, "End of program was reached properly.\n\n");
     fprintf(stderr, " ");
-    return 0;
+    return exit_code;
 }

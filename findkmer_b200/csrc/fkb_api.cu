@@ -269,7 +269,7 @@ static int pipeline_range_device(fkb_context *ctx, const uint8_t *fasta, size_t 
         FKB_CUDA(ctx, cudaStreamSynchronize(ctx->s_pipe));
         fkb::strip_state_read(ctx->h_strip_state, &out_off, &stop, &in_header);
         const bool last = (c + 1 == n_chunks) || stop != UINT64_MAX;
-        if (out_off > counted && (last || out_off - counted >= (96ull << 20))) {
+        if (k && out_off > counted && (last || out_off - counted >= (96ull << 20))) {  // k == 0: load only
             cudaError_t e = fkb::launch_count(launch_info(ctx), ctx->d_stream, counted, out_off, k, d_table, d_flags, d_partials, ctx->s_pipe, &launches);
             counted = out_off;
             FKB_CUDA(ctx, e);
@@ -393,7 +393,7 @@ static int pipeline_range(fkb_context *ctx, const uint8_t *fasta, size_t len, si
             *stop_offset = r.stop_pos;
         }
         const bool last = stopped || i + 1 == n_blocks;
-        if (cuda_err == cudaSuccess && dev_off > counted && (dev_off - counted >= count_every || last)) {
+        if (k && cuda_err == cudaSuccess && dev_off > counted && (dev_off - counted >= count_every || last)) {  // k == 0: load only
             int launches = 0;
             cuda_err = fkb::launch_count(launch_info(ctx), ctx->d_stream, counted, dev_off, k, d_table, d_flags, d_partials,
                                          ctx->s_pipe, &launches);
@@ -735,6 +735,78 @@ int fkb_count_fasta_host(fkb_context *ctx, const uint8_t *fasta, size_t len, int
         return fail(ctx, FKB_ERR_UNTERMINATED_HEADER, "%s", fkb_status_string(FKB_ERR_UNTERMINATED_HEADER));
     }
     return finish_host(ctx, k, stream_bytes, table, counts);
+}
+
+// The launcher's shape (k6thru11fullANDupstream.sh:16-24 runs one process per k over the same file) as ONE call: the file
+// crosses PCIe and is stripped once, then every k is counted over the device-resident stream.
+int fkb_count_fasta_host_multi(fkb_context *ctx, const uint8_t *fasta, size_t len, const int *ks, int n_k, uint32_t *const *tables,
+                               fkb_counts *counts)
+{
+    if (!ctx || !ks || n_k < 1 || !tables || !counts || (len && !fasta)) return FKB_ERR_BAD_ARG;
+    for (int i = 0; i < n_k; ++i) {
+        if (int s = check_k(ctx, ks[i])) return s;
+        if (!tables[i]) return FKB_ERR_BAD_ARG;
+    }
+    if (len == 0) return fail(ctx, FKB_ERR_EMPTY_INPUT, "Sequence File Is Empty");
+    FKB_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint64_t stream_bytes = 0, stop = 0;
+    int ends_in_header = 0;
+    if (int s = pipeline_range(ctx, fasta, len, 0, /*k=*/0, nullptr, nullptr, nullptr, &stream_bytes, &stop, &ends_in_header)) {  // load only
+        cudaStreamSynchronize(ctx->s_pipe);
+        return s;
+    }
+    if (ends_in_header) {
+        cudaStreamSynchronize(ctx->s_pipe);
+        return fail(ctx, FKB_ERR_UNTERMINATED_HEADER, "%s", fkb_status_string(FKB_ERR_UNTERMINATED_HEADER));
+    }
+    int worst = FKB_OK;
+    for (int i = 0; i < n_k; ++i) {
+        const int k = ks[i];
+        if (int s = ensure_table(ctx, k)) return s;
+        if (int s = ensure_bucket_scratch(ctx, k, stream_bytes)) return s;
+        if (int s = fkb_zero_device(ctx, k, ctx->d_table, ctx->d_flags, ctx->d_partials, ctx->s_pipe)) return s;
+        int launches = 0;
+        FKB_CUDA(ctx, fkb::launch_count(launch_info(ctx), ctx->d_stream, 16, 16 + stream_bytes, k, ctx->d_table, ctx->d_flags, ctx->d_partials,
+                                        ctx->s_pipe, &launches));
+        ctx->launches += launches;
+        int s = finish_host(ctx, k, stream_bytes, tables[i], &counts[i]);
+        if (s != FKB_OK && s != FKB_ERR_COUNTER_ROLLOVER) return s;
+        if (s != FKB_OK) worst = s;
+    }
+    return worst;
+}
+
+static int with_mapped_file(fkb_context *ctx, const char *path, const uint8_t **map_out, size_t *len_out)
+{
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(ctx, FKB_ERR_IO, "Sequence file failed to open: %s: %s", path, strerror(errno));
+    struct stat st;
+    if (fstat(fd, &st) != 0) {
+        close(fd);
+        return fail(ctx, FKB_ERR_IO, "fstat(%s): %s", path, strerror(errno));
+    }
+    if (st.st_size == 0) {
+        close(fd);
+        return fail(ctx, FKB_ERR_EMPTY_INPUT, "Sequence File Is Empty");
+    }
+    void *map = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (map == MAP_FAILED) return fail(ctx, FKB_ERR_IO, "mmap(%s): %s", path, strerror(errno));
+    madvise(map, (size_t)st.st_size, MADV_SEQUENTIAL | MADV_WILLNEED);
+    *map_out = (const uint8_t *)map;
+    *len_out = (size_t)st.st_size;
+    return FKB_OK;
+}
+
+int fkb_count_file_multi(fkb_context *ctx, const char *path, const int *ks, int n_k, uint32_t *const *tables, fkb_counts *counts)
+{
+    if (!ctx || !path) return FKB_ERR_BAD_ARG;
+    const uint8_t *map = nullptr;
+    size_t len = 0;
+    if (int s = with_mapped_file(ctx, path, &map, &len)) return s;
+    int s = fkb_count_fasta_host_multi(ctx, map, len, ks, n_k, tables, counts);
+    munmap((void *)map, len);
+    return s;
 }
 
 int fkb_count_file(fkb_context *ctx, const char *path, int k, uint32_t *table, fkb_counts *counts)

@@ -171,6 +171,20 @@ class KmerCounter:
         """An already stripped stream held on the host -> counts."""
         return self._host_call(self._lib.fkb_count_stream_host, data, k, table)
 
+    def count_fasta_multi(self, data, ks) -> list:
+        """Several k over one file image: uploaded and stripped once, counted per k (the launcher's k = 6..11 sweep)."""
+        ks = [int(k) for k in ks]
+        for k in ks:
+            if not (1 <= k <= _lib.FKB_MAX_K):
+                raise FindKmerError(_lib.FKB_ERR_BAD_K, f"{k} is not a valid value for k")
+        addr, n, keep = _host_view(data)
+        tables = [np.empty(4 ** k, dtype=np.uint32) for k in ks]
+        c_ks = (ctypes.c_int * len(ks))(*ks)
+        c_tables = (ctypes.c_void_p * len(ks))(*[t.ctypes.data for t in tables])
+        c_counts = (FkbCounts * len(ks))()
+        self._check(self._lib.fkb_count_fasta_host_multi(self._ctx, addr, n, c_ks, len(ks), c_tables, c_counts))
+        return [KmerCounts.from_struct(k, t, c_counts[i]) for i, (k, t) in enumerate(zip(ks, tables))]
+
     def count_file(self, path: str, k: int) -> KmerCounts:
         if not (1 <= k <= _lib.FKB_MAX_K):
             raise FindKmerError(_lib.FKB_ERR_BAD_K, f"{k} is not a valid value for k")

@@ -142,6 +142,14 @@ int fkb_count_stream_host(fkb_context *ctx, const uint8_t *stream, size_t len, i
 int fkb_count_fasta_host_range(fkb_context *ctx, const uint8_t *buf, size_t len, size_t own_offset, int k,
                                uint32_t *d_table, uint8_t *d_flags, fkb_partials *d_partials,
                                uint64_t *stream_bytes, uint64_t *stop_offset, int *ends_in_header);
+/* Several k over the same file image in one call -- the launcher's shape (k6thru11fullANDupstream.sh:16-24 starts one
+ * process per k on the same file): the bytes cross PCIe and are stripped ONCE, then every k is counted over the
+ * device-resident stream.  tables[i]: uint32[4^ks[i]] on the host; counts[i] likewise.  Returns the first hard error, or
+ * FKB_ERR_COUNTER_ROLLOVER if any k rolled over (the other results are valid). */
+int fkb_count_fasta_host_multi(fkb_context *ctx, const uint8_t *fasta, size_t len, const int *ks, int n_k,
+                               uint32_t *const *tables, fkb_counts *counts);
+int fkb_count_file_multi(fkb_context *ctx, const char *path, const int *ks, int n_k, uint32_t *const *tables,
+                         fkb_counts *counts);
 /* same, reading the file itself: the reference's `-p <file>` (:416-428, :344) */
 int fkb_count_file(fkb_context *ctx, const char *path, int k, uint32_t *table, fkb_counts *counts);
 

@@ -314,6 +314,18 @@ def test_device_loader_range_shards(device_loader, harness):
     assert_counts_equal(device_loader.finalize_device(acc, total), want)
 
 
+def test_multi_k_sweep_in_one_call(counter, harness):
+    """the launcher's k = 6..11 sweep (k6thru11fullANDupstream.sh:16-24) as one call: upload + strip once, count per k"""
+    from findkmer_b200 import synth
+    data = synth.render(synth.config2(n_bases=3_000_000))
+    for loader in (1, 2):
+        counter.set_loader(loader)
+        results = counter.count_fasta_multi(data, range(6, 12))
+        counter.set_loader(0)
+        for got in results:
+            assert_counts_equal(got, harness.oracle_count_fasta(data, got.k))
+
+
 # ---- loader / generator twins ---------------------------------------------------------------------------
 def test_device_generator_is_bit_identical_to_numpy(counter):
     from findkmer_b200 import synth
@@ -426,3 +438,21 @@ def test_cli_binary_is_a_drop_in(harness, tmp_path):
     assert (work / "7mer_Historam_Of_empty.fa.csv").read_bytes() == b"Sequence, Shannon Entropy h, Shannon Entropy H, Frequency, Z score"
     run = subprocess.run([str(exe), "-h"], cwd=work, capture_output=True, text=True, timeout=60)
     assert run.returncode == 1 and "Usage: findKmer [options]" in run.stdout
+
+
+def test_cli_k_sweep_extension(harness, tmp_path):
+    """`findKmer -K 6-8` == three separate reference runs (k6thru11fullANDupstream.sh's loop in one process)"""
+    import subprocess
+    from conftest import ROOT
+    from findkmer_b200 import synth
+    exe = ROOT / "findkmer_b200" / "bin" / "findKmer"
+    if not exe.exists() or not harness.reference_available():
+        pytest.skip("CLI or reference binary not built")
+    data = synth.render(synth.config3(n_records=300))
+    data.tofile(tmp_path / "up.fas")
+    run = subprocess.run([str(exe), "-q", "1", "-K", "6-8", "-z", "2", "-p", "up.fas"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stderr[-500:]
+    for k in (6, 7, 8):
+        ref = harness.run_reference(data, k, z=2, name="up.fas")
+        assert (tmp_path / ref.csv_name).read_bytes() == ref.csv
+        assert (tmp_path / ref.stats_name).read_bytes() == ref.stats
