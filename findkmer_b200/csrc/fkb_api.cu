@@ -104,7 +104,8 @@ int ensure_bucket_scratch(fkb_context *ctx, int k, uint64_t range_bytes)
     if (range_bytes < (64ull << 20) && ctx->forced_variant != fkb::VARIANT_BUCKET) return FKB_OK;  // the direct kernel will run
     const uint64_t items = range_bytes / S + 1;
     const uint64_t nb = (uint64_t)fkb::bucket_count(), n_cta = (uint64_t)ctx->sm_count;
-    uint64_t cap = (4 * (items / (nb * n_cta)) + 64 + 7) & ~7ull;
+    const uint64_t n_seg = n_cta * (uint64_t)fkb::bucket_segments_per_sm();
+    uint64_t cap = (4 * (items / (nb * n_seg)) + 64 + 7) & ~7ull;
     if (cap > 0x7FFFFFF8ull) cap = 0x7FFFFFF8ull;
     if (ctx->bucket.gbuf && ctx->bucket.cap_cb >= cap) return FKB_OK;
     if (ctx->bucket.gbuf) cudaFree(ctx->bucket.gbuf);
@@ -112,12 +113,12 @@ int ensure_bucket_scratch(fkb_context *ctx, int k, uint64_t range_bytes)
     ctx->bucket.cap_cb = 0;
     ctx->bucket.n_cta = (int)n_cta;
     if (!ctx->bucket.gcount) {
-        FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.gcount, nb * n_cta * sizeof(uint32_t)));
+        FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.gcount, nb * n_seg * sizeof(uint32_t)));
         FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.work, 64));
     }
     if (!ctx->bucket.table_w) FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.table_w, fkb::bucket_table_w_bytes()));
     if (!ctx->bucket.fold) FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.fold, fkb::bucket_fold_bytes()));
-    FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.gbuf, nb * n_cta * cap * sizeof(uint16_t)));
+    FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.gbuf, nb * n_seg * cap * sizeof(uint16_t)));
     ctx->bucket.cap_cb = (uint32_t)cap;
     return FKB_OK;
 }

@@ -35,7 +35,13 @@ namespace {
 constexpr int kW = 13;                       // counted word length
 constexpr int kBucketBits = 2 * kW - 16;     // 10
 constexpr int kNB = 1 << kBucketBits;        // 1024 buckets
-constexpr int kStageCap = 104;               // staged items per bucket (13 chunks of 8): 1024 rows of 208 B = 208 KiB
+#ifndef FKB_STAGE_CAP
+#define FKB_STAGE_CAP 104
+#endif
+#ifndef FKB_P1_MINBLOCKS
+#define FKB_P1_MINBLOCKS 1
+#endif
+constexpr int kStageCap = FKB_STAGE_CAP;       // staged items per bucket (13 chunks of 8): 1024 rows of 208 B = 208 KiB
 #ifndef FKB_TILE_AVG
 #define FKB_TILE_AVG 64
 #endif
@@ -44,6 +50,10 @@ constexpr int kStageCap = 104;               // staged items per bucket (13 chun
 #endif
 #ifndef FKB_P1_THREADS_HI
 #define FKB_P1_THREADS_HI 448  // measured best at S = 6
+#endif
+#ifndef FKB_RED_SLOTS
+#define FKB_RED_SLOTS 0u  // bit n set: slot n of every chunk bypasses the routing and goes to T_k with S global reds.  MEASURED NEGATIVE:
+                          // 1 slot of 16 already costs +10 % (a scattered global red occupies the LSU ~10x longer than a shared atomic)
 #endif
 #ifndef FKB_P2_THREADS
 #define FKB_P2_THREADS 1024
@@ -249,7 +259,7 @@ __device__ __noinline__ void escape_chunk(uint32_t bucket, uint4 v, uint32_t *ta
 }
 
 template <int S>
-__global__ void __launch_bounds__(P1Cfg<S>::kThreads, 1)
+__global__ void __launch_bounds__(P1Cfg<S>::kThreads, FKB_P1_MINBLOCKS)
 bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, uint16_t *__restrict__ gbuf, uint32_t cap_cb,
                  uint32_t *__restrict__ gcount, uint32_t *__restrict__ table_k, uint8_t *__restrict__ flags, fkb_partials *__restrict__ P)
 {
@@ -394,7 +404,15 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
                         constexpr int o0 = (kW - 1) % S;
                         const int o = o0 + n * S, g = o / 16 + 1, i = o % 16;
                         const uint32_t ca = cursor_sa + ((wc[n] >> 14) & 0xFFCu);  // &cursor[bucket]
-                        if constexpr (ALL) pos[n - 8 * h] = atoms_inc(ca);
+                        if ((FKB_RED_SLOTS >> n) & 1u) {  // folds after unrolling: n is a compile-time slot number
+                            // this slot goes straight to T_k: S reds on the L2-resident table
+                            const bool p = ALL || (emit[g] & (1u << (15 - i)));
+                            if (p) {
+#pragma unroll
+                                for (int t = 0; t < S; ++t) red_add_u32(table_k + ((wc[n] >> (2 * (S - 1 - t))) & KMASK), 1u);
+                            }
+                            pos[n - 8 * h] = 0xFFFFFFFFu;  // nothing to stage
+                        } else if constexpr (ALL) pos[n - 8 * h] = atoms_inc(ca);
                         else pos[n - 8 * h] = atoms_inc_if(ca, emit[g] & (1u << (15 - i)), kStageCap);
                     }
 #pragma unroll
@@ -405,7 +423,7 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
                         const uint32_t sa = stage_sa + bucket * (2u * kStageCap) + 2u * ps;
                         const uint32_t fits = ps < (uint32_t)kStageCap;
                         sts16_if(sa, wc[n], fits);
-                        const uint32_t emitted = ALL ? 1u : ((emit[g] >> (15 - i)) & 1u);
+                        const uint32_t emitted = ((FKB_RED_SLOTS >> n) & 1u) ? 0u : (ALL ? 1u : ((emit[g] >> (15 - i)) & 1u));
                         ovf |= (emitted & (fits ^ 1u)) << n;
                     }
                 }
@@ -671,8 +689,8 @@ cudaError_t run_bucketed(const LaunchInfo &li, const BucketScratch &bs, const ui
     const uint64_t n_witers = (hi - lo) / wspan;
     cudaError_t e = cudaMemsetAsync(bs.work, 0, 16, st);
     if (e != cudaSuccess) return e;
-    bucketize_kernel<S><<<bs.n_cta, P1Cfg<S>::kThreads, sizeof(P1Smem), st>>>(d_stream, lo, n_witers, bs.gbuf, bs.cap_cb, bs.gcount, d_table, d_flags, d_partials);
-    count_buckets_kernel<S><<<li.sm_count, kP2Threads, 128 * 1024, st>>>(bs.gbuf, bs.cap_cb, bs.gcount, bs.n_cta, bs.table_w, d_table, bs.work);
+    bucketize_kernel<S><<<bs.n_cta * FKB_P1_MINBLOCKS, P1Cfg<S>::kThreads, sizeof(P1Smem), st>>>(d_stream, lo, n_witers, bs.gbuf, bs.cap_cb, bs.gcount, d_table, d_flags, d_partials);
+    count_buckets_kernel<S><<<li.sm_count, kP2Threads, 128 * 1024, st>>>(bs.gbuf, bs.cap_cb, bs.gcount, bs.n_cta * FKB_P1_MINBLOCKS, bs.table_w, d_table, bs.work);
     if (launches) *launches += 2;
     cudaError_t e2 = cudaGetLastError();
     if (e2 != cudaSuccess) return e2;
@@ -697,6 +715,7 @@ size_t bucket_fold_bytes()
     return words * sizeof(uint32_t);
 }
 int bucket_count() { return kNB; }
+int bucket_segments_per_sm() { return FKB_P1_MINBLOCKS; }
 
 cudaError_t launch_count_bucketed(const LaunchInfo &li, const BucketScratch &bs, const uint8_t *d_stream, uint64_t lo, uint64_t hi, int k,
                                   uint32_t *d_table, uint8_t *d_flags, fkb_partials *d_partials, cudaStream_t st, int *launches)
