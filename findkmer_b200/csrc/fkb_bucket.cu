@@ -89,6 +89,21 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v)
     return v;
 }
 
+// Logical right shift by a constant.  The hot loops are bound by the ALU pipe (LOP3/SHF, ~70 % busy) while the FMA pipe
+// idles (~9 %): with FKB_SHR_VIA_IMAD the shift is issued as IMAD.HI (x * 2^(32-n) >> 32) on the FMA pipe instead.
+#ifndef FKB_SHR_VIA_IMAD
+#define FKB_SHR_VIA_IMAD 0
+#endif
+template <int N>
+__device__ __forceinline__ uint32_t shr_c(uint32_t x)
+{
+#if FKB_SHR_VIA_IMAD
+    return __umulhi(x, 1u << (32 - N));
+#else
+    return x >> N;
+#endif
+}
+
 // ---- SIMD-in-register encode of 4 ASCII bytes (one 32-bit word, byte 0 = lowest address) ----------------
 // codes: 8 bits, byte 0's 2-bit code in bits 7..6 (A0 C1 G2 T3 = base2int, findKmer.cpp:569-576)
 // bad  : a word whose byte i is ZERO iff input byte i is one of A,C,G,T.
@@ -96,9 +111,9 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v)
 //   b4 == q and b0 == ~q (A,C,G: q = 0 for A and C, 1 for G ... T: b2 = 1, b1 = 0 -> q = 1, b4 = 1, b0 = 0; G: b2 = b1 = 1 -> q = 0).
 __device__ __forceinline__ void encode_word(uint32_t w, uint32_t &codes, uint32_t &bad)
 {
-    const uint32_t p1 = w >> 1, p2 = w >> 2, p4 = w >> 4;
+    const uint32_t p1 = shr_c<1>(w), p2 = shr_c<2>(w), p4 = shr_c<4>(w);
     const uint32_t t = (p1 ^ p2) & 0x03030303u;
-    codes = (t * 0x40100401u) >> 24;
+    codes = shr_c<24>(t * 0x40100401u);
     const uint32_t q = p2 & ~p1;
     const uint32_t lo_bad = ((p4 ^ q) | ~(w ^ q)) & 0x01010101u;
     bad = ((w & 0xE8E8E8E8u) ^ 0x40404040u) | lo_bad;
@@ -403,7 +418,7 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
                     for (int n = 8 * h; n < 8 * h + 8; ++n) {
                         constexpr int o0 = (kW - 1) % S;
                         const int o = o0 + n * S, g = o / 16 + 1, i = o % 16;
-                        const uint32_t ca = cursor_sa + ((wc[n] >> 14) & 0xFFCu);  // &cursor[bucket]
+                        const uint32_t ca = cursor_sa + (shr_c<14>(wc[n]) & 0xFFCu);  // &cursor[bucket]
                         if ((FKB_RED_SLOTS >> n) & 1u) {  // folds after unrolling: n is a compile-time slot number
                             // this slot goes straight to T_k: S reds on the L2-resident table
                             const bool p = ALL || (emit[g] & (1u << (15 - i)));
@@ -419,7 +434,7 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
                     for (int n = 8 * h; n < 8 * h + 8; ++n) {
                         constexpr int o0 = (kW - 1) % S;
                         const int o = o0 + n * S, g = o / 16 + 1, i = o % 16;
-                        const uint32_t bucket = wc[n] >> 16, ps = pos[n - 8 * h];
+                        const uint32_t bucket = shr_c<16>(wc[n]), ps = pos[n - 8 * h];
                         const uint32_t sa = stage_sa + bucket * (2u * kStageCap) + 2u * ps;
                         const uint32_t fits = ps < (uint32_t)kStageCap;
                         sts16_if(sa, wc[n], fits);
