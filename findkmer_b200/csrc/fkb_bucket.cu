@@ -91,6 +91,18 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v)
 
 // Logical right shift by a constant.  The hot loops are bound by the ALU pipe (LOP3/SHF, ~70 % busy) while the FMA pipe
 // idles (~9 %): with FKB_SHR_VIA_IMAD the shift is issued as IMAD.HI (x * 2^(32-n) >> 32) on the FMA pipe instead.
+#ifndef FKB_OVF_VIA_MAX
+#define FKB_OVF_VIA_MAX 0
+#endif
+#ifndef FKB_ENC_V3
+#define FKB_ENC_V3 1  // fast encode: validity accumulated over the lane's whole chunk (left shifts go to the FMA pipe), one test per iteration
+#endif
+#ifndef FKB_ITEMS_V2
+#define FKB_ITEMS_V2 1  // W-mer left-aligned in the funnel-shifted word: bucket = word >> 22 (no masks), addresses by IMAD
+#endif
+#ifndef FKB_P2_V2
+#define FKB_P2_V2 1  // pass 2: drain test reduced to one AND per item (bit 15 of the counter's old value)
+#endif
 #ifndef FKB_SHR_VIA_IMAD
 #define FKB_SHR_VIA_IMAD 0
 #endif
@@ -156,6 +168,44 @@ __device__ __forceinline__ Group pack_group(const uint4 &g, uint32_t &unknown)
         unknown += 16 - __popc(r.valid) - nN - nH;
     }
     return r;
+}
+
+// ---- fast encode (FKB_ENC_V3): codes only; validity is ACCUMULATED over many words and tested once ----------------
+// A byte is one of A,C,G,T  <=>  b7 b6 b5 b3 = 0 1 0 0,  b4 == q,  b0 == ~q  with q = b2 & ~b1 (see encode_word).
+// The two relations are evaluated at bit 4 of every byte from LEFT-shifted copies of the word (left shifts are IMAD.SHL on
+// the otherwise idle FMA pipe, and shifting up never drags a neighbour byte's bits into bit 4); the four constant bits go
+// through an AND and an OR accumulator.  Per word: 1 shift + 1 mask + 1 multiply-gather for the codes, 3 IMAD.SHL + 4
+// LOP3 for the validity.
+struct ValidAcc {
+    uint32_t rel = 0;              // bit 4 of a byte set: b4 != q or b0 == q somewhere
+    uint32_t all = 0xFFFFFFFFu;    // AND of the words
+    uint32_t any = 0;              // OR of the words
+    __device__ __forceinline__ bool bad() const { return ((rel & 0x10101010u) | (any & 0xA8A8A8A8u) | (~all & 0x40404040u)) != 0; }
+};
+__device__ __forceinline__ uint32_t raw_index_gather(uint32_t w)  // top byte: (b2 b1) of byte 0 in bits 31..30, ... byte 3 in 25..24
+{
+    return ((w >> 1) & 0x03030303u) * 0x40100401u;
+}
+__device__ __forceinline__ void valid_acc_word(uint32_t w, ValidAcc &a)
+{
+    const uint32_t l2 = w << 2, l3 = w << 3, l4 = w << 4;
+    const uint32_t q = l2 & ~l3;
+    a.rel |= (w ^ q) | ~(l4 ^ q);
+}
+__device__ __forceinline__ uint32_t pack_codes_fast(const uint4 &g, ValidAcc &a)
+{
+    const uint32_t p0 = raw_index_gather(g.x), p1 = raw_index_gather(g.y), p2 = raw_index_gather(g.z), p3 = raw_index_gather(g.w);
+    valid_acc_word(g.x, a);
+    valid_acc_word(g.y, a);
+    valid_acc_word(g.z, a);
+    valid_acc_word(g.w, a);
+    a.all &= g.x & g.y;
+    a.all &= g.z & g.w;
+    a.any |= g.x | g.y;
+    a.any |= g.z | g.w;
+    const uint32_t t01 = __byte_perm(p1, p0, 0x0073), t23 = __byte_perm(p3, p2, 0x0073);  // byte 0 = later word's top byte, byte 1 = earlier word's
+    const uint32_t raw = __byte_perm(t23, t01, 0x5410);                                    // 16 raw indices: A0 C1 T2 G3
+    return raw ^ ((raw >> 1) & 0x55555555u);                                               // -> A0 C1 G2 T3
 }
 
 // bits b of m (earlier bytes in higher bits) such that bits b .. b+LEN-1 are all set, by doubling
@@ -240,6 +290,14 @@ __device__ __forceinline__ uint32_t atoms_inc_if(uint32_t saddr, uint32_t pred, 
     uint32_t old = if_not;
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p atom.shared.add.u32 %0, [%1], 1;\n\t}" : "+r"(old) : "r"(saddr), "r"(pred) : "memory");
     return old;
+}
+// a * b + c as ONE integer multiply-add (FMA pipe); written in PTX so that the address arithmetic of the staging code is not
+// re-associated into shift + mask pairs on the ALU pipe, which is the busier one in pass 1
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 }
 __device__ __forceinline__ uint32_t atoms_inc(uint32_t saddr)
 {
@@ -402,6 +460,39 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
             // ---- the 16 items of this chunk: static slots (slot n ends at chunk offset (W-1)%S + n*S), two batches of 8:
             //      8 shared atomics back to back (slot in the bucket's staging row), then 8 stores ----
             uint32_t ovf = 0;
+            // V2: the W-mer is LEFT-aligned in the funnel-shifted word f (bits 31..6; the low 6 bits are the next bases), so the
+            // bucket is f >> 22 with no mask, the two shared addresses are one IMAD each, and st.shared.u16 of f >> 6 stores the
+            // payload.  A full staging row is detected with one max per item; which slots overflowed is worked out off the hot path.
+            auto stage_items_v2 = [&](auto all_t) {
+                constexpr bool ALL = decltype(all_t)::value;
+                constexpr int o0 = (kW - 1) % S;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t f[8], bk[8], pos[8];
+#pragma unroll
+                    for (int n = 8 * h; n < 8 * h + 8; ++n) {
+                        const int o = o0 + n * S, g = o / 16 + 1, i = o % 16;
+                        const int sh = 2 * (15 - i);  // the W-mer ending at byte i of group g is bits [sh+25 : sh] of (grp[g-1].code : grp[g].code)
+                        f[n - 8 * h] = (sh >= 6) ? __funnelshift_r(grp[g].code, grp[g - 1].code, sh - 6) : (grp[g].code << (6 - sh));
+                        bk[n - 8 * h] = f[n - 8 * h] >> 22;
+                        const uint32_t ca = mad_u32(bk[n - 8 * h], 4u, cursor_sa);  // &cursor[bucket]
+                        if constexpr (ALL) pos[n - 8 * h] = atoms_inc(ca);
+                        else pos[n - 8 * h] = atoms_inc_if(ca, emit[g] & (1u << (15 - i)), 0xFFFFFFFFu);  // not emitted: no slot
+                    }
+                    uint32_t top = 0;  // max over the batch of (slot + 1); a slot that was not emitted contributes 0
+#pragma unroll
+                    for (int n = 0; n < 8; ++n) {
+                        const uint32_t ps = pos[n];
+                        const uint32_t sa = mad_u32(ps, 2u, mad_u32(bk[n], 2u * kStageCap, stage_sa));
+                        sts16_if(sa, f[n] >> 6, ps < (uint32_t)kStageCap);
+                        top = max(top, ps + 1u);
+                    }
+                    if (top > (uint32_t)kStageCap) {  // some staging row is full (skewed input): record which slots
+#pragma unroll
+                        for (int n = 0; n < 8; ++n) ovf |= (uint32_t)(pos[n] != 0xFFFFFFFFu && pos[n] >= (uint32_t)kStageCap) << (n + 8 * h);
+                    }
+                }
+            };
             auto stage_items = [&](auto all_t) {
                 constexpr bool ALL = decltype(all_t)::value;  // every slot is emitted: no predicates at all
                 uint32_t wc[16];
@@ -428,6 +519,26 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
                             }
                             pos[n - 8 * h] = 0xFFFFFFFFu;  // nothing to stage
                         } else if constexpr (ALL) pos[n - 8 * h] = atoms_inc(ca);
+#if FKB_OVF_VIA_MAX
+                        else pos[n - 8 * h] = atoms_inc_if(ca, emit[g] & (1u << (15 - i)), 0xFFFFFFFFu);  // not emitted: no slot
+                    }
+                    uint32_t top = 0;  // max over the batch of (slot + 1); a slot that was not emitted contributes 0
+#pragma unroll
+                    for (int n = 8 * h; n < 8 * h + 8; ++n) {
+                        const uint32_t bucket = shr_c<16>(wc[n]), ps = pos[n - 8 * h];
+                        const uint32_t sa = stage_sa + bucket * (2u * kStageCap) + 2u * ps;
+                        sts16_if(sa, wc[n], ps < (uint32_t)kStageCap);
+                        top = max(top, ps + 1u);
+                    }
+                    if (top > (uint32_t)kStageCap) {  // some staging row is full (skewed input): record which slots
+#pragma unroll
+                        for (int n = 8 * h; n < 8 * h + 8; ++n) {
+                            const uint32_t ps = pos[n - 8 * h];
+                            ovf |= (uint32_t)(ps != 0xFFFFFFFFu && ps >= (uint32_t)kStageCap) << n;
+                        }
+                    }
+                }
+#else
                         else pos[n - 8 * h] = atoms_inc_if(ca, emit[g] & (1u << (15 - i)), kStageCap);
                     }
 #pragma unroll
@@ -442,9 +553,15 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
                         ovf |= (emitted & (fits ^ 1u)) << n;
                     }
                 }
+#endif
             };
+#if FKB_ITEMS_V2
+            if (all_emit) stage_items_v2(std::true_type{});
+            else stage_items_v2(std::false_type{});
+#else
             if (all_emit) stage_items(std::true_type{});
             else stage_items(std::false_type{});
+#endif
             if (ovf) {  // skewed input: some staging row is full
                 uint32_t codes[S + 1];
 #pragma unroll
@@ -455,8 +572,20 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
             // ---- advance the pipeline ----
 #pragma unroll
             for (int g = 0; g < S; ++g) cur[g] = nxt[g];
+#if FKB_ENC_V3
+            {
+                ValidAcc va;
+#pragma unroll
+                for (int g = 0; g < S; ++g) { nxt[g].code = pack_codes_fast(raw[g], va); nxt[g].valid = 0xFFFFu; }
+                if (va.bad()) {  // some byte of this lane's 16*S is not a base: exact per-byte masks (and the unknown-character count)
+#pragma unroll
+                    for (int g = 0; g < S; ++g) nxt[g] = pack_group(raw[g], (it + 2 < my_iters) ? t_unknown : t_dummy);
+                }
+            }
+#else
 #pragma unroll
             for (int g = 0; g < S; ++g) nxt[g] = pack_group(raw[g], (it + 2 < my_iters) ? t_unknown : t_dummy);
+#endif
             issue_loads(it + 3);
         }
 
@@ -559,6 +688,46 @@ count_buckets_kernel(const uint16_t *__restrict__ gbuf, uint32_t cap_cb, const u
         // cross into its neighbour, whatever the interleaving of the other threads' updates: the increment that
         // sees 0x7FFF moves 32768 counts to T_k exactly and takes them out of the half again.
         // Eight items (one 128-bit load) at a time, branch-free: 8 shared atomics back to back, then 8 checks.
+#if FKB_P2_V2
+        // The drain is triggered by the increment that SEES 0x8000 (unique: the half then reads 0x8001 and the trigger takes
+        // 32768 out again), so the hot test is one AND per item: bit 15 of the half in the old value.  Whoever sees a half
+        // in 0x8001..0xFFFE while a drain is pending takes the slow path and finds nothing to do.
+        auto add8 = [&](const uint4 &v) {
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+            uint32_t old[8], top[8], any = 0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const uint32_t w = w4[e >> 1];
+                uint32_t sa, inc;
+                if (e & 1) {  // item in the high half-word
+                    sa = sub_sa + ((w >> 15) & 0x1FFFCu);
+                    inc = max(w & 0x10000u, 1u);           // odd index: the word's high counter
+                } else {
+                    sa = sub_sa + ((w << 1) & 0x1FFFCu);
+                    inc = (w & 1u) * 0xFFFFu + 1u;
+                }
+                top[e] = inc << 15;                         // bit 15 of the counter this item increments
+                asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old[e]) : "r"(sa), "r"(inc) : "memory");
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) any |= old[e] & top[e];
+            if (any) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const uint32_t idx = (e & 1) ? (w4[e >> 1] >> 16) : (w4[e >> 1] & 0xFFFFu);
+                    const uint32_t half = (idx & 1u) ? (old[e] >> 16) : (old[e] & 0xFFFFu);
+                    if (half == 0x8000u) drain_counter<S>(sub + (idx >> 1), idx & 1u, (b << 16) | idx, table_k);
+                }
+            }
+        };
+        auto add_item = [&](uint32_t idx) {
+            const uint32_t hi_half = idx & 1u;
+            uint32_t *word = sub + (idx >> 1);
+            const uint32_t old = atomicAdd(word, hi_half ? 0x10000u : 1u);
+            const uint32_t half = hi_half ? (old >> 16) : (old & 0xFFFFu);
+            if (half == 0x8000u) drain_counter<S>(word, hi_half, (b << 16) | idx, table_k);
+        };
+#else
         auto add8 = [&](const uint4 &v) {
             const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
             uint32_t old[8], sh[8], ovf = 0;
@@ -587,6 +756,7 @@ count_buckets_kernel(const uint16_t *__restrict__ gbuf, uint32_t cap_cb, const u
             const uint32_t half = hi_half ? (old >> 16) : (old & 0xFFFFu);
             if (half == 0x7FFFu) drain_counter<S>(word, hi_half, (b << 16) | idx, table_k);
         };
+#endif
         for (;;) {
             uint32_t seg = 0;
             if (lane == 0) seg = atomicAdd(&s_next_seg, 1u);
