@@ -78,6 +78,14 @@ __device__ __forceinline__ uint4 ldg128(const uint8_t *p)
     asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
+// predicated 128-bit load (zeros when off): no branch, so the loads stay inside the basic block of the staging code
+__device__ __forceinline__ uint4 ldg128_if(const uint8_t *p, bool pred)
+{
+    uint4 r = make_uint4(0, 0, 0, 0);
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
+                 : "+r"(r.x), "+r"(r.y), "+r"(r.z), "+r"(r.w) : "l"(p), "r"((uint32_t)pred));
+    return r;
+}
 __device__ __forceinline__ void red_add_u32(uint32_t *addr, uint32_t v)
 {
     asm volatile("red.global.add.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
@@ -342,7 +350,6 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
     constexpr int K = kW - S + 1;
     constexpr int CH = 16 * S;                     // bytes per lane per iteration: exactly 16 items
     constexpr int J = S - 1;
-    constexpr uint32_t WMASK = (1u << (2 * kW)) - 1u;
     constexpr uint32_t KMASK = (1u << (2 * K)) - 1u;
     constexpr uint64_t WSPAN = 32ull * CH;
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -354,78 +361,78 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
     if (threadIdx.x < 16) sm.ev[threadIdx.x] = 0;
     __syncthreads();
 
-    // this warp's contiguous share of the interior
+    // this warp's contiguous share of the interior (the host keeps n_witers below 2^32: launch_count_bucketed)
     const uint64_t n_warps = (uint64_t)gridDim.x * kP1Warps, gw = (uint64_t)blockIdx.x * kP1Warps + warp;
     const uint64_t q = n_witers / n_warps, rem = n_witers % n_warps;
-    const uint64_t my_iters = q + (gw < rem ? 1 : 0);
+    const uint32_t my_iters = (uint32_t)(q + (gw < rem ? 1 : 0));
     const uint64_t my_first = gw * q + (gw < rem ? gw : rem);
-    const uint64_t max_iters = q + (rem ? 1 : 0);          // CTA-uniform trip count (barriers)
+    const uint32_t max_iters = (uint32_t)(q + (rem ? 1 : 0));  // CTA-uniform trip count (barriers)
     const uint64_t region = lo + my_first * WSPAN, hi = lo + n_witers * WSPAN;
     uint16_t *const my_gbuf = gbuf + (uint64_t)blockIdx.x * cap_cb;  // + bucket * gridDim.x * cap_cb
+    // the two chunks of the interior whose windows meet a range edge: lane 0 of the first iteration, lane 31 of the last
+    const bool edge_first = (lane == 0) && (region == lo), edge_last = (lane == 31) && (region + (uint64_t)my_iters * WSPAN == hi);
 
-    uint32_t t_unknown = 0, t_dummy = 0;
+    uint32_t t_unknown = 0, t_dummy = 0, n_fast = 0;
     unsigned long long t_windows = 0, t_valid = 0;
 
     // ---- software pipeline: `cur` = packed groups of iteration it, `nxt` = of it+1, `raw` = loads of it+2 in flight ----
-    Group cur[S], nxt[S], carry;   // carry: the 16 bytes in front of lane 0's chunk (previous iteration's lane 31, last group)
+    // Group g of iteration `it` of this lane lies at region + it*WSPAN + lane*CH + 16*g.  Iteration my_iters consists of lane 0's
+    // first group only (the right halo of the region); beyond it there is nothing (zero bytes: not bases).
+    Group cur[S], nxt[S], carry;   // carry (lane 0 only): the 16 bytes in front of lane 0's chunk = previous iteration's lane 31, last group
     uint4 raw[S];
-    auto issue_loads = [&](uint64_t it) {  // it == my_iters: only lane 0's first group (the right halo of the region); beyond: nothing
-        const uint64_t base = region + it * WSPAN + (uint64_t)lane * CH;
-        if (it < my_iters) {
-#pragma unroll
-            for (int g = 0; g < S; ++g) raw[g] = ldg128(s + base + 16 * g);
-        } else {
-#pragma unroll
-            for (int g = 0; g < S; ++g) raw[g] = make_uint4(0, 0, 0, 0);
-            if (it == my_iters && lane == 0) raw[0] = ldg128(s + base);
-        }
+    const uint8_t *const lane_base = s + region + (uint64_t)lane * CH;
+    auto load_group = [&](uint32_t it, int g) -> uint4 {
+        const bool p = (it < my_iters) || (g == 0 && it == my_iters && lane == 0);
+        return ldg128_if(lane_base + (uint64_t)it * WSPAN + 16 * g, p);
     };
     {
         carry = pack_group(ldg128(s + region - 16), t_dummy);  // left halo of the region (same address for all lanes)
-        issue_loads(0);
 #pragma unroll
-        for (int g = 0; g < S; ++g) cur[g] = pack_group(raw[g], my_iters > 0 ? t_unknown : t_dummy);
-        issue_loads(1);
+        for (int g = 0; g < S; ++g) cur[g] = pack_group(load_group(0, g), my_iters > 0 ? t_unknown : t_dummy);
 #pragma unroll
-        for (int g = 0; g < S; ++g) nxt[g] = pack_group(raw[g], my_iters > 1 ? t_unknown : t_dummy);
-        issue_loads(2);
+        for (int g = 0; g < S; ++g) nxt[g] = pack_group(load_group(1, g), my_iters > 1 ? t_unknown : t_dummy);
+#pragma unroll
+        for (int g = 0; g < S; ++g) raw[g] = load_group(2, g);
     }
 
-    for (uint64_t tile0 = 0; tile0 < max_iters; tile0 += kTileIters) {
-        for (uint64_t it = tile0; it < tile0 + kTileIters && it < my_iters; ++it) {
-            // ---- neighbours: grp[0] = 16 bytes before my chunk, grp[1..S] = my chunk, grp[S+1] = 16 bytes after it ----
+    for (uint32_t tile0 = 0; tile0 < max_iters; tile0 += kTileIters) {
+        const uint32_t tile_end = min(tile0 + (uint32_t)kTileIters, my_iters);
+        for (uint32_t it = tile0; it < tile_end; ++it) {
+            // ---- neighbours: grp[0] = 16 bytes before my chunk, grp[1..S] = my chunk, grp[S+1] = 16 bytes after it.
+            //      Two rotations: lane L takes the last group of lane L-1 (lane 0 receives lane 31's, which is the NEXT iteration's
+            //      carry) and the first group of lane L+1 (lane 31 receives lane 0's first group of the next iteration). ----
             Group grp[S + 2];
 #pragma unroll
             for (int g = 0; g < S; ++g) grp[g + 1] = cur[g];
-            grp[0].code = __shfl_up_sync(0xffffffffu, cur[S - 1].code, 1);
-            grp[0].valid = __shfl_up_sync(0xffffffffu, cur[S - 1].valid, 1);
-            grp[S + 1].code = __shfl_down_sync(0xffffffffu, cur[0].code, 1);
-            grp[S + 1].valid = __shfl_down_sync(0xffffffffu, cur[0].valid, 1);
-            const uint32_t n0c = __shfl_sync(0xffffffffu, nxt[0].code, 0), n0v = __shfl_sync(0xffffffffu, nxt[0].valid, 0);
-            const uint32_t l31c = __shfl_sync(0xffffffffu, cur[S - 1].code, 31), l31v = __shfl_sync(0xffffffffu, cur[S - 1].valid, 31);
-            if (lane == 0) grp[0] = carry;
-            if (lane == 31) { grp[S + 1].code = n0c; grp[S + 1].valid = n0v; }
-            carry.code = l31c;
-            carry.valid = l31v;
+            const uint32_t up_c = __shfl_sync(0xffffffffu, cur[S - 1].code, (lane + 31) & 31);
+            const uint32_t dn_c = __shfl_sync(0xffffffffu, lane == 0 ? nxt[0].code : cur[0].code, (lane + 1) & 31);
+            grp[0].code = lane == 0 ? carry.code : up_c;
+            grp[S + 1].code = dn_c;
+            const bool is_lo = edge_first && it == 0, is_hi = edge_last && it + 1 == my_iters;
 
-            const uint64_t cbase = region + it * WSPAN + (uint64_t)lane * CH;
-            uint32_t vall = grp[0].valid & grp[S + 1].valid;
+            uint32_t own = cur[0].valid;
 #pragma unroll
-            for (int g = 1; g <= S; ++g) vall &= grp[g].valid;
-            const bool edge = (cbase == lo) || (cbase + CH == hi);
-
+            for (int g = 1; g < S; ++g) own &= cur[g].valid;
+            if (lane == 0) own &= carry.valid & nxt[0].valid;  // the two neighbours that are not another lane's own groups
             uint32_t emit[S + 2];
             // warp-uniform choice: if any lane needs the general path the whole warp takes it (it is correct for clean
             // chunks too); a per-lane branch would execute both paths back to back on soft-masked / N-rich input
-            const bool all_emit = __all_sync(0xffffffffu, vall == 0xFFFFu && !edge);
+            const bool all_emit = __all_sync(0xffffffffu, own == 0xFFFFu && !(is_lo || is_hi));
             if (all_emit) {
-                // ---- fast path: 16*(S+2) valid bases around me: every anchored window exists, nothing is left over ----
+                // ---- fast path: 16*(S+2) valid bases around every lane: every anchored window exists, nothing is left over ----
 #pragma unroll
                 for (int g = 0; g < S + 2; ++g) emit[g] = 0;
-                t_windows += 16 * S;
-                t_valid += 16 * S;
+                ++n_fast;
+                carry.code = up_c;  // lane 0: lane 31's last group
+                carry.valid = 0xFFFFu;
             } else {
                 // ---- general path: window masks per group; emit = fully valid W-window ending at an anchored position ----
+                const uint32_t up_v = __shfl_sync(0xffffffffu, cur[S - 1].valid, (lane + 31) & 31);
+                const uint32_t dn_v = __shfl_sync(0xffffffffu, lane == 0 ? nxt[0].valid : cur[0].valid, (lane + 1) & 31);
+                grp[0].valid = lane == 0 ? carry.valid : up_v;
+                grp[S + 1].valid = dn_v;
+                carry.code = up_c;
+                carry.valid = up_v;
 #pragma unroll
                 for (int g = 1; g <= S + 1; ++g) {
                     const uint32_t m = (grp[g - 1].valid << 16) | grp[g].valid;
@@ -435,8 +442,8 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
                         if ((16 * (g - 1) + i) % S == (kW - 1) % S) phase |= 1u << (15 - i);
                     emit[g] = runs_of<kW>(m) & phase;
                 }
-                if (cbase + CH == hi) emit[S + 1] = 0;        // windows ending beyond hi belong to nobody here: their k-mers are leftovers
-                if (cbase == lo) emit[1] &= (0xFFFFu >> J);   // a window whose first covered k-mer ends before lo is not ours
+                if (is_hi) emit[S + 1] = 0;               // windows ending beyond hi belong to nobody here: their k-mers are leftovers
+                if (is_lo) emit[1] &= (0xFFFFu >> J);     // a window whose first covered k-mer ends before lo is not ours
 #pragma unroll
                 for (int g = 1; g <= S; ++g) {
                     const uint32_t m = (grp[g - 1].valid << 16) | grp[g].valid;
@@ -458,13 +465,18 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
             }
 
             // ---- the 16 items of this chunk: static slots (slot n ends at chunk offset (W-1)%S + n*S), two batches of 8:
-            //      8 shared atomics back to back (slot in the bucket's staging row), then 8 stores ----
+            //      8 shared atomics back to back (slot in the bucket's staging row), then 8 stores.  The W-mer is LEFT-aligned in
+            //      the funnel-shifted word f (bits 31..6; the low 6 bits are the next bases): the bucket is f >> 22 with no mask,
+            //      the two shared addresses are one IMAD each, and st.shared.u16 of f >> 6 stores the payload.
+            //      BETWEEN the atomics and the stores that wait for their results, the lane encodes its groups of iteration it+2
+            //      (ALU/FMA work that hides the shared-memory latency) and re-issues their loads for it+3. ----
             uint32_t ovf = 0;
-            // V2: the W-mer is LEFT-aligned in the funnel-shifted word f (bits 31..6; the low 6 bits are the next bases), so the
-            // bucket is f >> 22 with no mask, the two shared addresses are one IMAD each, and st.shared.u16 of f >> 6 stores the
-            // payload.  A full staging row is detected with one max per item; which slots overflowed is worked out off the hot path.
-            auto stage_items_v2 = [&](auto all_t) {
-                constexpr bool ALL = decltype(all_t)::value;
+            ValidAcc va;
+            Group enc[S];
+            const bool ld_full = it + 3 < my_iters, ld_halo = (it + 3 == my_iters) && lane == 0;
+            const uint8_t *const p3 = lane_base + (uint64_t)(it + 3) * WSPAN;
+            auto stage_items = [&](auto all_t) {
+                constexpr bool ALL = decltype(all_t)::value;  // every slot is emitted: no predicates at all
                 constexpr int o0 = (kW - 1) % S;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -479,6 +491,13 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
                         if constexpr (ALL) pos[n - 8 * h] = atoms_inc(ca);
                         else pos[n - 8 * h] = atoms_inc_if(ca, emit[g] & (1u << (15 - i)), 0xFFFFFFFFu);  // not emitted: no slot
                     }
+#pragma unroll
+                    for (int g = 0; g < S; ++g)
+                        if (g * 2 / S == h) {
+                            enc[g].code = pack_codes_fast(raw[g], va);
+                            enc[g].valid = 0xFFFFu;
+                            raw[g] = ldg128_if(p3 + 16 * g, ld_full || (g == 0 && ld_halo));
+                        }
                     uint32_t top = 0;  // max over the batch of (slot + 1); a slot that was not emitted contributes 0
 #pragma unroll
                     for (int n = 0; n < 8; ++n) {
@@ -493,100 +512,22 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
                     }
                 }
             };
-            auto stage_items = [&](auto all_t) {
-                constexpr bool ALL = decltype(all_t)::value;  // every slot is emitted: no predicates at all
-                uint32_t wc[16];
-#pragma unroll
-                for (int n = 0; n < 16; ++n) {
-                    constexpr int o0 = (kW - 1) % S;
-                    const int o = o0 + n * S, g = o / 16 + 1, i = o % 16;
-                    wc[n] = __funnelshift_r(grp[g].code, grp[g - 1].code, 2 * (15 - i)) & WMASK;
-                }
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t pos[8];
-#pragma unroll
-                    for (int n = 8 * h; n < 8 * h + 8; ++n) {
-                        constexpr int o0 = (kW - 1) % S;
-                        const int o = o0 + n * S, g = o / 16 + 1, i = o % 16;
-                        const uint32_t ca = cursor_sa + (shr_c<14>(wc[n]) & 0xFFCu);  // &cursor[bucket]
-                        if ((FKB_RED_SLOTS >> n) & 1u) {  // folds after unrolling: n is a compile-time slot number
-                            // this slot goes straight to T_k: S reds on the L2-resident table
-                            const bool p = ALL || (emit[g] & (1u << (15 - i)));
-                            if (p) {
-#pragma unroll
-                                for (int t = 0; t < S; ++t) red_add_u32(table_k + ((wc[n] >> (2 * (S - 1 - t))) & KMASK), 1u);
-                            }
-                            pos[n - 8 * h] = 0xFFFFFFFFu;  // nothing to stage
-                        } else if constexpr (ALL) pos[n - 8 * h] = atoms_inc(ca);
-#if FKB_OVF_VIA_MAX
-                        else pos[n - 8 * h] = atoms_inc_if(ca, emit[g] & (1u << (15 - i)), 0xFFFFFFFFu);  // not emitted: no slot
-                    }
-                    uint32_t top = 0;  // max over the batch of (slot + 1); a slot that was not emitted contributes 0
-#pragma unroll
-                    for (int n = 8 * h; n < 8 * h + 8; ++n) {
-                        const uint32_t bucket = shr_c<16>(wc[n]), ps = pos[n - 8 * h];
-                        const uint32_t sa = stage_sa + bucket * (2u * kStageCap) + 2u * ps;
-                        sts16_if(sa, wc[n], ps < (uint32_t)kStageCap);
-                        top = max(top, ps + 1u);
-                    }
-                    if (top > (uint32_t)kStageCap) {  // some staging row is full (skewed input): record which slots
-#pragma unroll
-                        for (int n = 8 * h; n < 8 * h + 8; ++n) {
-                            const uint32_t ps = pos[n - 8 * h];
-                            ovf |= (uint32_t)(ps != 0xFFFFFFFFu && ps >= (uint32_t)kStageCap) << n;
-                        }
-                    }
-                }
-#else
-                        else pos[n - 8 * h] = atoms_inc_if(ca, emit[g] & (1u << (15 - i)), kStageCap);
-                    }
-#pragma unroll
-                    for (int n = 8 * h; n < 8 * h + 8; ++n) {
-                        constexpr int o0 = (kW - 1) % S;
-                        const int o = o0 + n * S, g = o / 16 + 1, i = o % 16;
-                        const uint32_t bucket = shr_c<16>(wc[n]), ps = pos[n - 8 * h];
-                        const uint32_t sa = stage_sa + bucket * (2u * kStageCap) + 2u * ps;
-                        const uint32_t fits = ps < (uint32_t)kStageCap;
-                        sts16_if(sa, wc[n], fits);
-                        const uint32_t emitted = ((FKB_RED_SLOTS >> n) & 1u) ? 0u : (ALL ? 1u : ((emit[g] >> (15 - i)) & 1u));
-                        ovf |= (emitted & (fits ^ 1u)) << n;
-                    }
-                }
-#endif
-            };
-#if FKB_ITEMS_V2
-            if (all_emit) stage_items_v2(std::true_type{});
-            else stage_items_v2(std::false_type{});
-#else
             if (all_emit) stage_items(std::true_type{});
             else stage_items(std::false_type{});
-#endif
-            if (ovf) {  // skewed input: some staging row is full
+            if (ovf) {  // exact escape of the items that found their staging row full
                 uint32_t codes[S + 1];
 #pragma unroll
                 for (int g = 0; g <= S; ++g) codes[g] = grp[g].code;
                 escape_slots<S>(ovf, codes, table_k);
             }
+            if (va.bad()) {  // some byte of this lane's 16*S is not a base: exact per-byte masks (and the unknown-character count) from a re-read
+#pragma unroll
+                for (int g = 0; g < S; ++g) enc[g] = pack_group(load_group(it + 2, g), (it + 2 < my_iters) ? t_unknown : t_dummy);
+            }
 
             // ---- advance the pipeline ----
 #pragma unroll
-            for (int g = 0; g < S; ++g) cur[g] = nxt[g];
-#if FKB_ENC_V3
-            {
-                ValidAcc va;
-#pragma unroll
-                for (int g = 0; g < S; ++g) { nxt[g].code = pack_codes_fast(raw[g], va); nxt[g].valid = 0xFFFFu; }
-                if (va.bad()) {  // some byte of this lane's 16*S is not a base: exact per-byte masks (and the unknown-character count)
-#pragma unroll
-                    for (int g = 0; g < S; ++g) nxt[g] = pack_group(raw[g], (it + 2 < my_iters) ? t_unknown : t_dummy);
-                }
-            }
-#else
-#pragma unroll
-            for (int g = 0; g < S; ++g) nxt[g] = pack_group(raw[g], (it + 2 < my_iters) ? t_unknown : t_dummy);
-#endif
-            issue_loads(it + 3);
+            for (int g = 0; g < S; ++g) { cur[g] = nxt[g]; nxt[g] = enc[g]; }
         }
 
         // ---- flush: append whole 16-byte chunks of every staged row to this CTA's region of the bucket ----
@@ -647,6 +588,8 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
         }
         gcount[(uint64_t)b * gridDim.x + blockIdx.x] = off;
     }
+    t_windows += (unsigned long long)n_fast * (16 * S);
+    t_valid += (unsigned long long)n_fast * (16 * S);
     t_windows = warp_sum(t_windows);
     t_valid = warp_sum(t_valid);
     unsigned long long t_unk = warp_sum((unsigned long long)t_unknown);
