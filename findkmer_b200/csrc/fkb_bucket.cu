@@ -541,36 +541,45 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
             }
         }
         {
-            const uint32_t sub = lane >> 3, c = lane & 7;  // 4 buckets per warp step, 8 lanes each
+            // A warp takes 32 buckets at a time.  (A) one lane per bucket: fill, region offset and the <= 7 items that stay
+            // staged; (B) 8 lanes per bucket, 4 buckets per step: 128-bit copies of the whole chunks (fill and offset come
+            // from the owning lane in one shuffle); (C) one lane per bucket again: the tail goes to the front of the row.
+            // Scalar work costs one shared-memory wavefront per 32 buckets this way instead of one per 4.
+            const uint32_t sub = lane >> 3, c = lane & 7;
             const uint64_t bstride = (uint64_t)gridDim.x * cap_cb;
-            for (uint32_t b = warp * 4 + sub; b < (uint32_t)kNB; b += kP1Warps * 4) {
-                const uint32_t cnt = min(sm.cursor[b], (uint32_t)kStageCap);
-                const uint32_t n8 = cnt & ~7u, off = sm.goff[b];
-                uint16_t *row = &sm.stage[b * kStageCap];
-                uint16_t *dst = my_gbuf + b * bstride + off;
+            for (uint32_t b0 = warp * 32; b0 < (uint32_t)kNB; b0 += kP1Warps * 32) {
+                const uint32_t bl = b0 + lane;
+                const uint32_t cnt = min(sm.cursor[bl], (uint32_t)kStageCap);
+                const uint32_t n8 = cnt & ~7u, off = sm.goff[bl];  // off is a multiple of 8 below 2^31
+                const bool has_tail = n8 && cnt > n8;
                 uint4 tail = make_uint4(0, 0, 0, 0);
-                const bool has_tail = (c == 0) && n8 && cnt > n8;
-                uint32_t esc = 0;
-                if (has_tail) tail = *reinterpret_cast<const uint4 *>(row + n8);  // the <= 7 items that stay staged
+                if (has_tail) tail = *reinterpret_cast<const uint4 *>(&sm.stage[bl * kStageCap + n8]);
+                const uint32_t packed = (off >> 3) | ((n8 >> 3) << 28);
 #pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    const uint32_t ci = c + 8 * cc, i0 = ci * 8u;
-                    if (i0 < n8) {
-                        const uint4 v = *reinterpret_cast<const uint4 *>(row + i0);
-                        if (off + i0 + 8 <= cap_cb) *reinterpret_cast<uint4 *>(dst + i0) = v;
-                        else esc |= 1u << cc;
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t pk = __shfl_sync(0xffffffffu, packed, 4 * j + sub);
+                    const uint32_t b = b0 + 4 * j + sub, n8b = (pk >> 28) << 3, offb = (pk & 0x0FFFFFFFu) << 3;
+                    const uint16_t *row = &sm.stage[b * kStageCap];
+                    uint16_t *dst = my_gbuf + b * bstride + offb;
+                    uint32_t esc = 0;
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const uint32_t i0 = (c + 8 * cc) * 8u;
+                        if (i0 < n8b) {
+                            const uint4 v = *reinterpret_cast<const uint4 *>(row + i0);
+                            if (offb + i0 + 8 <= cap_cb) *reinterpret_cast<uint4 *>(dst + i0) = v;
+                            else esc |= 1u << cc;
+                        }
+                    }
+                    if (esc) {  // this CTA's region of the bucket is full (heavily skewed input): exact escape, off the copy loop
+                        for (int cc = 0; cc < 2; ++cc)
+                            if (esc & (1u << cc)) escape_chunk<S>(b, *reinterpret_cast<const uint4 *>(row + (c + 8 * cc) * 8u), table_k);
                     }
                 }
-                if (esc) {  // this CTA's region of the bucket is full (heavily skewed input): exact escape, off the copy loop
-                    for (int cc = 0; cc < 2; ++cc)
-                        if (esc & (1u << cc)) escape_chunk<S>(b, *reinterpret_cast<const uint4 *>(row + (c + 8 * cc) * 8u), table_k);
-                }
                 __syncwarp();
-                if (c == 0) {
-                    if (has_tail) *reinterpret_cast<uint4 *>(row) = tail;
-                    sm.cursor[b] = cnt - n8;
-                    sm.goff[b] = min(off + n8, cap_cb & ~7u);
-                }
+                if (has_tail) *reinterpret_cast<uint4 *>(&sm.stage[bl * kStageCap]) = tail;
+                sm.cursor[bl] = cnt - n8;
+                sm.goff[bl] = min(off + n8, cap_cb & ~7u);
             }
         }
         __syncthreads();
