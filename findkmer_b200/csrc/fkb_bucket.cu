@@ -231,6 +231,29 @@ __device__ __forceinline__ uint32_t runs_of(uint32_t m)
     }
 }
 
+// ---- item format -----------------------------------------------------------------------------------------------
+// A W-mer is 26 bits  [ a : A = 2(S-1) bits | core : 10 bits | r : R = 16 - A bits ].  With S <= kCoreMaxS the BUCKET is the
+// core -- the 5 bases that every one of the S k-mers inside the W-mer contains -- and the payload is (a, r).  All W-mers that
+// contribute to one k-mer x at offset t then sit in ONE bucket (core = x's bases S-1-t .. S+3-t), so pass 2 folds its 65536
+// counters to k-mer counts in shared memory and adds S * 4^(K-5) sums to T_k: the 4^W-entry W-mer table and the fold
+// kernels over it disappear.  For larger S (k <= 8) the k-mers of a W-mer share fewer than 5 bases: bucket = top 10 bits,
+// payload = low 16 bits, and the W-mer table is folded by the fold kernels below.
+#ifndef FKB_CORE_MAX_S
+#define FKB_CORE_MAX_S 5
+#endif
+constexpr int kCoreMaxS = FKB_CORE_MAX_S;
+template <int S> struct ItemFmt {
+    static constexpr bool kCore = (S <= kCoreMaxS) && (S <= 5);
+    __host__ __device__ static constexpr int a_bits() { return kCore ? 2 * (S - 1) : 0; }  // bits of the W-mer above the bucket bits
+    __host__ __device__ static constexpr int r_bits() { return 16 - a_bits(); }             // bits below them
+    __host__ __device__ static constexpr uint32_t rmask() { return (1u << r_bits()) - 1u; }
+    __device__ __forceinline__ static uint32_t wmer(uint32_t bucket, uint32_t payload)  // (bucket, payload) -> 26-bit W-mer code
+    {
+        if constexpr (kCore) return ((payload >> r_bits()) << (r_bits() + 10)) | (bucket << r_bits()) | (payload & rmask());
+        else return (bucket << 16) | payload;
+    }
+};
+
 // S k-mers of one W-mer: every exact escape (staging overflow, region overflow, counter drain) goes through here
 template <int S>
 __device__ __noinline__ void red_kmers_of_word(uint32_t wcode, uint32_t *table_k, uint32_t amount)
@@ -336,7 +359,7 @@ template <int S>
 __device__ __noinline__ void escape_chunk(uint32_t bucket, uint4 v, uint32_t *table_k)
 {
     const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-    for (int e = 0; e < 8; ++e) red_kmers_of_word<S>((bucket << 16) | ((w4[e >> 1] >> (16 * (e & 1))) & 0xFFFFu), table_k, 1u);
+    for (int e = 0; e < 8; ++e) red_kmers_of_word<S>(ItemFmt<S>::wmer(bucket, (w4[e >> 1] >> (16 * (e & 1))) & 0xFFFFu), table_k, 1u);
 }
 
 template <int S>
@@ -485,8 +508,13 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
                     for (int n = 8 * h; n < 8 * h + 8; ++n) {
                         const int o = o0 + n * S, g = o / 16 + 1, i = o % 16;
                         const int sh = 2 * (15 - i);  // the W-mer ending at byte i of group g is bits [sh+25 : sh] of (grp[g-1].code : grp[g].code)
-                        f[n - 8 * h] = (sh >= 6) ? __funnelshift_r(grp[g].code, grp[g - 1].code, sh - 6) : (grp[g].code << (6 - sh));
-                        bk[n - 8 * h] = f[n - 8 * h] >> 22;
+                        if constexpr (ItemFmt<S>::kCore) {  // right-aligned: bits 25..0; the core starts A bits below the top
+                            f[n - 8 * h] = __funnelshift_r(grp[g].code, grp[g - 1].code, sh);
+                            bk[n - 8 * h] = (f[n - 8 * h] << (6 + ItemFmt<S>::a_bits())) >> 22;
+                        } else {                            // left-aligned: bits 31..6; the bucket is the top 10 bits
+                            f[n - 8 * h] = (sh >= 6) ? __funnelshift_r(grp[g].code, grp[g - 1].code, sh - 6) : (grp[g].code << (6 - sh));
+                            bk[n - 8 * h] = f[n - 8 * h] >> 22;
+                        }
                         const uint32_t ca = mad_u32(bk[n - 8 * h], 4u, cursor_sa);  // &cursor[bucket]
                         if constexpr (ALL) pos[n - 8 * h] = atoms_inc(ca);
                         else pos[n - 8 * h] = atoms_inc_if(ca, emit[g] & (1u << (15 - i)), 0xFFFFFFFFu);  // not emitted: no slot
@@ -503,7 +531,10 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
                     for (int n = 0; n < 8; ++n) {
                         const uint32_t ps = pos[n];
                         const uint32_t sa = mad_u32(ps, 2u, mad_u32(bk[n], 2u * kStageCap, stage_sa));
-                        sts16_if(sa, f[n] >> 6, ps < (uint32_t)kStageCap);
+                        uint32_t pay;  // only the low 16 bits are stored
+                        if constexpr (ItemFmt<S>::kCore) pay = (f[n] & ItemFmt<S>::rmask()) | ((f[n] >> 10) & ~ItemFmt<S>::rmask());  // (a, r)
+                        else pay = f[n] >> 6;
+                        sts16_if(sa, pay, ps < (uint32_t)kStageCap);
                         top = max(top, ps + 1u);
                     }
                     if (top > (uint32_t)kStageCap) {  // some staging row is full (skewed input): record which slots
@@ -593,7 +624,7 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
         for (uint32_t i = 0; i < cnt; ++i) {
             const uint16_t item = sm.stage[stage_slot(b, i)];
             if (off < cap_cb) dst[off++] = item;
-            else red_kmers_of_word<S>(((uint32_t)b << 16) | item, table_k, 1u);
+            else red_kmers_of_word<S>(ItemFmt<S>::wmer((uint32_t)b, item), table_k, 1u);
         }
         gcount[(uint64_t)b * gridDim.x + blockIdx.x] = off;
     }
@@ -613,6 +644,60 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
 // pass 2: per bucket, 65536 16-bit counters in shared memory; one shared atomicAdd per item.
 // The bucket's items lie in n_seg CTA-private segments; warps take whole segments.
 // ------------------------------------------------------------------------------------------------
+// ---- pass 2 epilogue with core buckets: fold the bucket's 65536 W-mer counters to k-mer counts in shared memory ----
+// Counter index = payload = (a : A bits | r : R bits); the bucket b is the core.  The k-mer at offset t of the W-mer
+// [a | core | r] drops the top 2t bits of a and the low A-2t bits of r:  x_t = [a_lo | core | r_hi], so
+//   T_k[x_t] += sum over a_hi (4^t slabs) and r_lo (an aligned run of 4^(S-1-t) consecutive counters).
+// Every counter is read S times (vector loads for the runs, dp2a to add the 16-bit halves); consecutive threads produce
+// consecutive k-mers, so the S * 2^R global reds of a bucket are coalesced (32 lanes per 128-byte line).
+template <int NU16>
+__device__ __forceinline__ uint32_t sum_u16_run(const uint16_t *p)  // NU16 consecutive counters, aligned to their size
+{
+    if constexpr (NU16 == 1) {
+        return *p;
+    } else if constexpr (NU16 == 4) {
+        const uint2 v = *reinterpret_cast<const uint2 *>(p);
+        return __dp2a_lo(v.y, 0x0101u, __dp2a_lo(v.x, 0x0101u, 0u));
+    } else {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < NU16 / 8; ++i) {
+            const uint4 v = reinterpret_cast<const uint4 *>(p)[i];
+            acc = __dp2a_lo(v.x, 0x0101u, acc);
+            acc = __dp2a_lo(v.y, 0x0101u, acc);
+            acc = __dp2a_lo(v.z, 0x0101u, acc);
+            acc = __dp2a_lo(v.w, 0x0101u, acc);
+        }
+        return acc;
+    }
+}
+template <int S, int T>
+__device__ __forceinline__ void fold_core_offset(const uint16_t *cnt, uint32_t b, uint32_t *table_k)
+{
+    constexpr int A = ItemFmt<S>::a_bits(), R = ItemFmt<S>::r_bits();
+    constexpr int LO = A - 2 * T;   // bits of r that are summed over
+    constexpr int HI = 2 * T;       // bits of a that are summed over
+    constexpr int RH = R - LO;      // bits of r that stay
+    for (uint32_t o = threadIdx.x; o < (1u << R); o += kP2Threads) {
+        const uint32_t r_hi = o & ((1u << RH) - 1u), a_lo = o >> RH;
+        uint32_t sum = 0;
+#pragma unroll 4
+        for (uint32_t a_hi = 0; a_hi < (1u << HI); ++a_hi) {
+            const uint32_t a = (a_hi << LO) | a_lo;  // A bits: a_hi on top (HI bits), a_lo below (A - HI = LO bits)
+            sum += sum_u16_run<(1 << LO)>(cnt + ((a << R) | (r_hi << LO)));
+        }
+        if (sum) red_add_u32(table_k + ((a_lo << (10 + RH)) | (b << RH) | r_hi), sum);
+    }
+}
+template <int S, int T = 0>
+__device__ __forceinline__ void fold_core_bucket(const uint16_t *cnt, uint32_t b, uint32_t *table_k)
+{
+    if constexpr (T < S) {
+        fold_core_offset<S, T>(cnt, b, table_k);
+        fold_core_bucket<S, T + 1>(cnt, b, table_k);
+    }
+}
+
 template <int S>
 __device__ __noinline__ void drain_counter(uint32_t *word, uint32_t hi_half, uint32_t wcode, uint32_t *table_k)
 {
@@ -668,7 +753,7 @@ count_buckets_kernel(const uint16_t *__restrict__ gbuf, uint32_t cap_cb, const u
                 for (int e = 0; e < 8; ++e) {
                     const uint32_t idx = (e & 1) ? (w4[e >> 1] >> 16) : (w4[e >> 1] & 0xFFFFu);
                     const uint32_t half = (idx & 1u) ? (old[e] >> 16) : (old[e] & 0xFFFFu);
-                    if (half == 0x8000u) drain_counter<S>(sub + (idx >> 1), idx & 1u, (b << 16) | idx, table_k);
+                    if (half == 0x8000u) drain_counter<S>(sub + (idx >> 1), idx & 1u, ItemFmt<S>::wmer(b, idx), table_k);
                 }
             }
         };
@@ -677,7 +762,7 @@ count_buckets_kernel(const uint16_t *__restrict__ gbuf, uint32_t cap_cb, const u
             uint32_t *word = sub + (idx >> 1);
             const uint32_t old = atomicAdd(word, hi_half ? 0x10000u : 1u);
             const uint32_t half = hi_half ? (old >> 16) : (old & 0xFFFFu);
-            if (half == 0x8000u) drain_counter<S>(word, hi_half, (b << 16) | idx, table_k);
+            if (half == 0x8000u) drain_counter<S>(word, hi_half, ItemFmt<S>::wmer(b, idx), table_k);
         };
 #else
         auto add8 = [&](const uint4 &v) {
@@ -697,7 +782,7 @@ count_buckets_kernel(const uint16_t *__restrict__ gbuf, uint32_t cap_cb, const u
                 for (int e = 0; e < 8; ++e)
                     if (ovf & (1u << e)) {
                         const uint32_t idx = (e & 1) ? (w4[e >> 1] >> 16) : (w4[e >> 1] & 0xFFFFu);
-                        drain_counter<S>(sub + (idx >> 1), idx & 1u, (b << 16) | idx, table_k);
+                        drain_counter<S>(sub + (idx >> 1), idx & 1u, ItemFmt<S>::wmer(b, idx), table_k);
                     }
             }
         };
@@ -706,7 +791,7 @@ count_buckets_kernel(const uint16_t *__restrict__ gbuf, uint32_t cap_cb, const u
             uint32_t *word = sub + (idx >> 1);
             const uint32_t old = atomicAdd(word, hi_half ? 0x10000u : 1u);
             const uint32_t half = hi_half ? (old >> 16) : (old & 0xFFFFu);
-            if (half == 0x7FFFu) drain_counter<S>(word, hi_half, (b << 16) | idx, table_k);
+            if (half == 0x7FFFu) drain_counter<S>(word, hi_half, ItemFmt<S>::wmer(b, idx), table_k);
         };
 #endif
         for (;;) {
@@ -729,8 +814,12 @@ count_buckets_kernel(const uint16_t *__restrict__ gbuf, uint32_t cap_cb, const u
             if ((uint32_t)lane < n - n8) add_item(items[n8 + lane]);
         }
         __syncthreads();
-        uint4 *out = reinterpret_cast<uint4 *>(table_w + ((uint64_t)b << 16));
-        for (int i = threadIdx.x; i < 32768 / 4; i += kP2Threads) out[i] = reinterpret_cast<const uint4 *>(sub)[i];
+        if constexpr (ItemFmt<S>::kCore) {
+            fold_core_bucket<S>(reinterpret_cast<const uint16_t *>(sub), b, table_k);
+        } else {
+            uint4 *out = reinterpret_cast<uint4 *>(table_w + ((uint64_t)b << 16));
+            for (int i = threadIdx.x; i < 32768 / 4; i += kP2Threads) out[i] = reinterpret_cast<const uint4 *>(sub)[i];
+        }
         __syncthreads();
     }
 }
@@ -831,7 +920,8 @@ cudaError_t run_bucketed(const LaunchInfo &li, const BucketScratch &bs, const ui
     if (launches) *launches += 2;
     cudaError_t e2 = cudaGetLastError();
     if (e2 != cudaSuccess) return e2;
-    return run_fold<S>(li, bs, d_table, st, launches);
+    if constexpr (ItemFmt<S>::kCore) return cudaSuccess;  // pass 2 has already folded every bucket into T_k
+    else return run_fold<S>(li, bs, d_table, st, launches);
 }
 
 }  // namespace
