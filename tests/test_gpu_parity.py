@@ -214,7 +214,7 @@ def test_bucketed_variant_short_records(bucketed, harness, k):
     assert_counts_equal(got, harness.oracle_count_stream(stream, k))
 
 
-@pytest.mark.parametrize("k", [8, 11])
+@pytest.mark.parametrize("k", [8, 9, 11, 13])
 def test_bucketed_variant_skewed_input_exercises_every_escape(bucketed, harness, k):
     """poly-A with sparse substitutions: one bucket takes almost everything -> staging rows overflow, the bucket's
     region in HBM overflows, and 16-bit counters drain at 0x8000; every escape must stay exact"""
@@ -395,6 +395,17 @@ def test_full_size_properties(counter):
     split = counter.finalize_device(acc2, n)
     assert np.array_equal(split.table, whole.table)
     assert (split.n_kmers, split.base_count, split.node_count) == (whole.n_kmers, whole.base_count, whole.node_count)
+    # the two count paths share no counting code (bucketed: routed 13-mers folded in shared memory; direct: one global red
+    # per window, checked against the oracle at small sizes): their full-size tables must be identical bin for bin
+    counter.set_variant(1)
+    try:
+        acc3 = counter.new_accumulators(k)
+        counter.count_stream_device(d, k, acc3)
+        direct = counter.finalize_device(acc3, n)
+    finally:
+        counter.set_variant(0)
+    assert np.array_equal(direct.table, whole.table)
+    assert (direct.n_kmers, direct.base_count, direct.node_count) == (whole.n_kmers, whole.base_count, whole.node_count)
     del d
     torch.cuda.empty_cache()
 
