@@ -281,17 +281,23 @@ def main():
     achieved = shard_bytes / (kernel_ms * 1e-3) / 1e9
     # DRAM traffic of the same launch sequence, from the committed ncu capture (profiles/r01_traffic_k11.json:
     # dram__bytes_read.sum + dram__bytes_write.sum of every kernel of one step; it cannot be measured live)
-    traffic, traffic_note = None, None
+    traffic, traffic_note, shares = None, None, None
     tpath = ROOT / "profiles" / "r01_traffic_k11.json"
     if tpath.exists() and world == 1 and k == 11 and args.bases == N_BASES:
         tj = json.loads(tpath.read_text())
         traffic = tj["dram_bytes_per_step"]
-        traffic_note = ("ncu capture " + tpath.name + ": 2.6x the algorithmic bytes BY DESIGN -- the routed 16-bit payloads are written "
-                        "and read once (2 x 2/3 B/base) and the 13-mer table once (128 MiB + fold reads); no re-reads of the stream")
+        traffic_note = ("ncu capture " + tpath.name + f": {traffic / shard_bytes:.1f}x the algorithmic bytes BY DESIGN -- the routed 16-bit "
+                        "payloads are written and read once (2 x 2/3 B/base); the stream itself is read exactly once and there is "
+                        "no 13-mer table in HBM any more (pass 2 folds in shared memory)")
+        count_kernels = [kk for kk in tj["kernels"] if not kk["kernel"].startswith("finalize")]
+        tot_us = sum(kk["us"] for kk in count_kernels) or 1.0
+        shares = " + ".join(f"{kk['kernel']} ({100 * kk['us'] / tot_us:.0f} %)" for kk in sorted(count_kernels, key=lambda x: -x["us"]))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "count path of one step: bucketize_kernel<3> (69 % of the time) + count_buckets_kernel<3> (24 %) + fold (4 %) + edges",
+                "kernel": "count path of one step: " + (shares or "bucketize_kernel + count_buckets_kernel + edges (shares: profiles/)"),
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": shard_bytes, "peak_source": peak_src, "traffic_note": traffic_note,
-                "binding_resource": "shared-memory LSU pipe ~70-74 % and ALU pipe ~68-75 % busy in both kernels (ncu); scattered-RMW bound, not HBM bound"}
+                "binding_resource": "shared-memory data pipe (l1tex LSU wavefronts) ~80 % busy in both kernels, bank conflicts of random "
+                                    "32-lane accesses (3.5 wavefronts per shared atomic / 16-bit store); ALU ~57 %; DRAM ~45 % of the copy "
+                                    "bandwidth: scattered-RMW bound, not HBM bound (profiles/README.md)"}
 
     # ---- e2e leg: raw FASTA bytes in pinned host memory -> counts on the host ----
     e2e = None

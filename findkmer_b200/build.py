@@ -6,6 +6,7 @@ Outputs (git-ignored, but they travel to the GPU box with the snapshot):
     findkmer_b200/libfindkmer_b200.so   the extern "C" library of include/findkmer_b200.h
     findkmer_b200/bin/findKmer          the drop-in command line program
     findkmer_b200/bin/fkb_ubench        atomic-throughput micro-benchmarks (profiling aid)
+    findkmer_b200/bin/fkb_ubench_bulk   staging-row flush: LSU copies vs cp.async.bulk (profiling aid)
 """
 from __future__ import annotations
 
@@ -66,10 +67,11 @@ def build(verbose: bool = False, force: bool = False) -> Path:
     exe = BIN / "findKmer"
     if main_src.exists() and (force or _stale(exe, [main_src, LIB] + headers)):
         _run(["g++"] + CXX_FLAGS + [main_src, "-o", exe, "-L", PKG, "-lfindkmer_b200", "-Wl,-rpath,$ORIGIN/..", "-lpthread"], verbose)
-    ub_src = CSRC / "fkb_ubench.cu"
-    ub = BIN / "fkb_ubench"
-    if ub_src.exists() and (force or _stale(ub, [ub_src] + headers)):
-        _run([NVCC] + NVCC_FLAGS + [ub_src, "-o", ub], verbose)
+    for name in ("fkb_ubench", "fkb_ubench_bulk"):
+        ub_src = CSRC / (name + ".cu")
+        ub = BIN / name
+        if ub_src.exists() and (force or _stale(ub, [ub_src] + headers)):
+            _run([NVCC] + NVCC_FLAGS + [ub_src, "-o", ub], verbose)
     return LIB
 
 
