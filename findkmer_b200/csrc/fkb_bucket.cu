@@ -9,21 +9,24 @@
 //   (S-1-t)-base suffixes b) of T_W[a x b],  plus the few "leftover" k-mers whose covering W-window is broken
 //   by a reset or a range edge (those go straight to T_k with a global red).  At k = 11 that is 3x fewer items.
 //
-//   pass 1  bucketize : every warp streams a contiguous region of the stream, software-pipelined one iteration
-//                       ahead (128-bit loads).  Fused ASCII->2-bit encode + validity (SIMD in 32-bit registers,
-//                       16 bases per word) + window extraction; item = 26-bit W-mer code, bucket = top 10 bits
-//                       (1024 buckets), payload = low 16 bits.  Items are staged per bucket in shared memory (the
-//                       shared atomicAdd returns the slot) and appended, in 16-byte chunks, to a region of HBM that
-//                       is private to (bucket, CTA) -- no global atomics on the routing path.
+//   pass 1  bucketize : every warp streams a contiguous region of the stream, software-pipelined (128-bit loads).
+//                       Fused ASCII->2-bit encode + validity (SIMD in 32-bit registers, validity accumulated over
+//                       the lane's chunk and tested once) + window extraction; item = 26-bit W-mer code split into
+//                       a 10-bit bucket and a 16-bit payload (see "item format").  Items are staged per bucket in
+//                       shared memory (the shared atomicAdd returns the slot) and appended, in 16-byte chunks, to a
+//                       region of HBM that is private to (bucket, CTA) -- no global atomics on the routing path.
 //   pass 2  count     : one CTA at a time owns a bucket's 65536 16-bit counters (128 KiB of shared memory), streams
 //                       the bucket's payloads with 128-bit loads and counts with shared-memory atomics; a counter
-//                       that reaches 0x8000 drains exactly to T_k.  The sub-table is written out once.
+//                       that passes 0x8000 drains exactly to T_k.  k >= 9 (core buckets): the counters are folded
+//                       to k-mer sums in shared memory and added to T_k.  k <= 8: the sub-table goes to T_W and
 //   pass 3  fold      : T_k[x] += gathered sums of T_W (coalesced reads, no atomics).
 //
 // Semantics are those of the reference's scan (findKmer/src/findKmer.cpp:962-1069) exactly; the rare per-run
 // events (seqSize == k, :1044-1057; seqSize < k, :1059-1062) are derived from the validity bit masks.
 // profiles/r01_ncu_bucketize_v1_by_line.txt is the instruction profile of the first version of pass 1 that this
-// layout answers (38 % of instructions in the flush copy loop, 15 % in run-mask loops, a barrier per iteration).
+// layout answers (38 % of instructions in the flush copy loop, 15 % in run-mask loops, a barrier per iteration);
+// profiles/r01_ncu_full_summary.txt is where it stands: both passes bound by the shared-memory data pipe (bank
+// conflicts of random 32-lane accesses, 3.5 wavefronts per atomic / 16-bit store).
 #include <type_traits>
 
 #include "fkb_kernels.cuh"
