@@ -89,6 +89,20 @@ __device__ __forceinline__ uint4 ldg128_if(const uint8_t *p, bool pred)
                  : "+r"(r.x), "+r"(r.y), "+r"(r.z), "+r"(r.w) : "l"(p), "r"((uint32_t)pred));
     return r;
 }
+// predicated 128-bit shared load / global store (pass-1 flush): no branches, loads and stores in separate statements so
+// that a step's loads are all in flight before the first store waits for its data
+__device__ __forceinline__ uint4 lds128_if(uint32_t saddr, bool pred)
+{
+    uint4 r = make_uint4(0, 0, 0, 0);
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
+                 : "+r"(r.x), "+r"(r.y), "+r"(r.z), "+r"(r.w) : "r"(saddr), "r"((uint32_t)pred));
+    return r;
+}
+__device__ __forceinline__ void stg128_if(void *gptr, const uint4 &v, bool pred)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q st.global.v4.u32 [%0], {%1,%2,%3,%4};\n\t}"
+                 ::"l"(gptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"((uint32_t)pred) : "memory");
+}
 __device__ __forceinline__ void red_add_u32(uint32_t *addr, uint32_t v)
 {
     asm volatile("red.global.add.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
@@ -421,8 +435,15 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
         for (int g = 0; g < S; ++g) raw[g] = load_group(2, g);
     }
 
-    for (uint32_t tile0 = 0; tile0 < max_iters; tile0 += kTileIters) {
-        const uint32_t tile_end = min(tile0 + (uint32_t)kTileIters, my_iters);
+    // Tiles (the iterations between two flushes) are kTileIters long, except the first one: CTA i starts with 1 + i mod kTileIters
+    // iterations, so that the 148 CTAs -- which all have the same amount of work -- do not flush at the same moment (a flush is
+    // a burst of 128 KiB of writes per CTA; in lockstep the bursts collide in L2/HBM while the write path idles in between).
+#ifndef FKB_STAGGER
+#define FKB_STAGGER 1
+#endif
+    for (uint32_t tile0 = 0, tile_len = FKB_STAGGER ? 1u + blockIdx.x % (uint32_t)kTileIters : (uint32_t)kTileIters; tile0 < max_iters;
+         tile0 += tile_len, tile_len = kTileIters) {
+        const uint32_t tile_end = min(tile0 + tile_len, my_iters);
         for (uint32_t it = tile0; it < tile_end; ++it) {
             // ---- neighbours: grp[0] = 16 bytes before my chunk, grp[1..S] = my chunk, grp[S+1] = 16 bytes after it.
             //      Two rotations: lane L takes the last group of lane L-1 (lane 0 receives lane 31's, which is the NEXT iteration's
@@ -580,40 +601,47 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
             // from the owning lane in one shuffle); (C) one lane per bucket again: the tail goes to the front of the row.
             // Scalar work costs one shared-memory wavefront per 32 buckets this way instead of one per 4.
             const uint32_t sub = lane >> 3, c = lane & 7;
-            const uint64_t bstride = (uint64_t)gridDim.x * cap_cb;
+            uint32_t n_seg;  // gridDim.x, read here so that the flush's invariants do not occupy registers across the streaming loop
+            asm volatile("mov.u32 %0, %%nctaid.x;" : "=r"(n_seg));
+            const uint64_t bstride = (uint64_t)n_seg * cap_cb;
+            const uint32_t cap8 = cap_cb & ~7u;
             for (uint32_t b0 = warp * 32; b0 < (uint32_t)kNB; b0 += kP1Warps * 32) {
                 const uint32_t bl = b0 + lane;
                 const uint32_t cnt = min(sm.cursor[bl], (uint32_t)kStageCap);
-                const uint32_t n8 = cnt & ~7u, off = sm.goff[bl];  // off is a multiple of 8 below 2^31
+                const uint32_t n8 = cnt & ~7u, off = sm.goff[bl];  // off is a multiple of 8, <= cap8 < 2^31
+                const uint32_t ncp = min(n8, cap8 - off);          // items of whole chunks that still fit this CTA's region
                 const bool has_tail = n8 && cnt > n8;
                 uint4 tail = make_uint4(0, 0, 0, 0);
                 if (has_tail) tail = *reinterpret_cast<const uint4 *>(&sm.stage[bl * kStageCap + n8]);
-                const uint32_t packed = (off >> 3) | ((n8 >> 3) << 28);
+                const uint32_t packed = (off >> 3) | ((ncp >> 3) << 28);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t pk = __shfl_sync(0xffffffffu, packed, 4 * j + sub);
-                    const uint32_t b = b0 + 4 * j + sub, n8b = (pk >> 28) << 3, offb = (pk & 0x0FFFFFFFu) << 3;
-                    const uint16_t *row = &sm.stage[b * kStageCap];
-                    uint16_t *dst = my_gbuf + b * bstride + offb;
-                    uint32_t esc = 0;
+                for (int jj = 0; jj < 8; jj += 4) {  // 4 steps of 4 buckets at a time: shuffles, then all loads, then all stores
+                    uint32_t pk[4];
+                    uint4 v[8];
 #pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) {
-                        const uint32_t i0 = (c + 8 * cc) * 8u;
-                        if (i0 < n8b) {
-                            const uint4 v = *reinterpret_cast<const uint4 *>(row + i0);
-                            if (offb + i0 + 8 <= cap_cb) *reinterpret_cast<uint4 *>(dst + i0) = v;
-                            else esc |= 1u << cc;
-                        }
+                    for (int j = 0; j < 4; ++j) pk[j] = __shfl_sync(0xffffffffu, packed, 4 * (jj + j) + sub);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t ncb = (pk[j] >> 28) << 3;
+                        const uint32_t row_sa = stage_sa + ((b0 + 4 * (jj + j) + sub) * kStageCap + c * 8u) * 2u;  // this lane's chunk of the row
+                        v[2 * j] = lds128_if(row_sa, c * 8u < ncb);
+                        v[2 * j + 1] = lds128_if(row_sa + 128u, c * 8u + 64u < ncb);
                     }
-                    if (esc) {  // this CTA's region of the bucket is full (heavily skewed input): exact escape, off the copy loop
-                        for (int cc = 0; cc < 2; ++cc)
-                            if (esc & (1u << cc)) escape_chunk<S>(b, *reinterpret_cast<const uint4 *>(row + (c + 8 * cc) * 8u), table_k);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t ncb = (pk[j] >> 28) << 3, offb = (pk[j] & 0x0FFFFFFFu) << 3;
+                        uint16_t *dst = my_gbuf + (uint64_t)(b0 + 4 * (jj + j) + sub) * bstride + offb + c * 8u;
+                        stg128_if(dst, v[2 * j], c * 8u < ncb);
+                        stg128_if(dst + 64, v[2 * j + 1], c * 8u + 64u < ncb);
                     }
                 }
                 __syncwarp();
+                if (ncp < n8) {  // this CTA's region of the bucket is full (heavily skewed input): exact escape, off the copy loop
+                    for (uint32_t i0 = ncp; i0 < n8; i0 += 8) escape_chunk<S>(bl, *reinterpret_cast<const uint4 *>(&sm.stage[bl * kStageCap + i0]), table_k);
+                }
                 if (has_tail) *reinterpret_cast<uint4 *>(&sm.stage[bl * kStageCap]) = tail;
                 sm.cursor[bl] = cnt - n8;
-                sm.goff[bl] = min(off + n8, cap_cb & ~7u);
+                sm.goff[bl] = off + ncp;
             }
         }
         __syncthreads();

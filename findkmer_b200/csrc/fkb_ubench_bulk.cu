@@ -71,16 +71,18 @@ int main()
     CK(cudaEventCreate(&e1));
     const int tiles = 200;
     const int rings[] = {1, 64};  // 1: every tile rewrites the same 19-30 MB (stays in L2); 64: streams to HBM like the real kernel
+    const int grids[] = {sms, (sms + 7) / 8};  // every SM flushing at once vs one SM in eight (is the limit per SM or chip-wide?)
+    for (int gi = 0; gi < 2; ++gi)
     for (int ri = 0; ri < 2; ++ri) {
-        const int ring = rings[ri];
+        const int ring = rings[ri], grid = grids[gi];
         uint8_t *dst;
         CK(cudaMalloc(&dst, (size_t)kRows * sms * ring * 208));
         for (int row_bytes = 64; row_bytes <= 208; row_bytes += (row_bytes == 128 ? 80 : 64)) {
             for (int mode = 0; mode < 2; ++mode) {
                 for (int rep = 0; rep < 2; ++rep) {
                     CK(cudaEventRecord(e0));
-                    if (mode == 0) k_flush_lsu<<<sms, kThreads, smem>>>(dst, row_bytes, tiles, ring);
-                    else k_flush_bulk<<<sms, kThreads, smem>>>(dst, row_bytes, tiles, ring);
+                    if (mode == 0) k_flush_lsu<<<grid, kThreads, smem>>>(dst, row_bytes, tiles, ring);
+                    else k_flush_bulk<<<grid, kThreads, smem>>>(dst, row_bytes, tiles, ring);
                     CK(cudaEventRecord(e1));
                     CK(cudaEventSynchronize(e1));
                     CK(cudaGetLastError());
@@ -88,9 +90,9 @@ int main()
                 float ms;
                 CK(cudaEventElapsedTime(&ms, e0, e1));
                 const double us_tile = ms * 1e3 / tiles;
-                printf("{\"bench\": \"%s\", \"ring\": %d, \"row_bytes\": %d, \"us_per_tile\": %.3f, \"clk_per_row\": %.2f, \"chip_gbs\": %.0f}\n",
-                       mode ? "flush_bulk" : "flush_lsu", ring, row_bytes, us_tile, us_tile * 1e-6 * prop.clockRate * 1e3 / kRows,
-                       (double)sms * kRows * row_bytes / us_tile * 1e-3);
+                printf("{\"bench\": \"%s\", \"ctas\": %d, \"ring\": %d, \"row_bytes\": %d, \"us_per_tile\": %.3f, \"clk_per_row\": %.2f, \"chip_gbs\": %.0f}\n",
+                       mode ? "flush_bulk" : "flush_lsu", grid, ring, row_bytes, us_tile, us_tile * 1e-6 * prop.clockRate * 1e3 / kRows,
+                       (double)grid * kRows * row_bytes / us_tile * 1e-3);
             }
         }
         CK(cudaFree(dst));
