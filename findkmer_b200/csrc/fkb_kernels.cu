@@ -205,83 +205,17 @@ __global__ void __launch_bounds__(kThreads) count_direct_kernel(const uint8_t *_
 //   scratch[5..8]   sum of table over k-mers whose FIRST base is b   (depth-1 trie node visits, :640)
 //   scratch[9]      number of trie nodes below the head
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) finalize_table_kernel(const uint32_t *__restrict__ table, int k, uint8_t *__restrict__ flags,
-                                                                  unsigned long long *__restrict__ scratch)
+// The trie node at depth d with prefix x exists iff a short run set flags[d][x] or one of its four children exists
+// (depth k: table[x] != 0).  One launch takes an INPUT level d_in (LEAF: the table, 4 leaves per thread; otherwise the flag
+// bytes of depth d_in, 4 siblings per thread) and resolves three levels with warp ballots -- thread = node at depth
+// d_in-1, 32 lanes = 8 nodes at depth d_in-2 = 2 nodes at depth d_in-3 -- counting the nodes of depths d_in, d_in-1 and
+// d_in-2 and writing the presence of depth d_in-3, which is the next launch's input: ceil(k/3) launches instead of k.
+// The launch that reaches depth 1 is a single block and also assembles fkb_counts.
+__device__ void finalize_counts(const unsigned long long *scratch_g, const fkb_partials *__restrict__ P, uint64_t stream_bytes,
+                                fkb_counts *__restrict__ out)
 {
-    const uint64_t groups = 1ull << (2 * (k - 1));  // groups of 4 sibling leaves
-    unsigned long long tot = 0, last[4] = {0, 0, 0, 0}, first[4] = {0, 0, 0, 0}, nodes = 0;
-    for (uint64_t g = (uint64_t)blockIdx.x * kThreads + threadIdx.x; g < groups; g += (uint64_t)gridDim.x * kThreads) {
-        uint4 v = reinterpret_cast<const uint4 *>(table)[g];
-        unsigned long long sum = (unsigned long long)v.x + v.y + v.z + v.w;
-        tot += sum;
-        last[0] += v.x; last[1] += v.y; last[2] += v.z; last[3] += v.w;
-        if (k == 1) {
-            first[0] += v.x; first[1] += v.y; first[2] += v.z; first[3] += v.w;
-        } else {
-            uint32_t fb = (uint32_t)(g >> (2 * (k - 2)));
-            first[0] += (fb == 0) ? sum : 0; first[1] += (fb == 1) ? sum : 0;
-            first[2] += (fb == 2) ? sum : 0; first[3] += (fb == 3) ? sum : 0;
-        }
-        nodes += (v.x != 0) + (v.y != 0) + (v.z != 0) + (v.w != 0);
-        if (k > 1 && sum != 0) flags[flags_offset(k - 1) + g] = 1;
-    }
-    // block-level reduction: one set of 10 global atomics per CTA instead of per warp (they all hit the same 10 words)
-    unsigned long long vals[10] = {tot, last[0], last[1], last[2], last[3], first[0], first[1], first[2], first[3], nodes};
-    __shared__ unsigned long long red[kThreads / 32][10];
-#pragma unroll
-    for (int i = 0; i < 10; ++i) vals[i] = warp_sum(vals[i]);
-    if ((threadIdx.x & 31) == 0)
-        for (int i = 0; i < 10; ++i) red[threadIdx.x >> 5][i] = vals[i];
-    __syncthreads();
-    if (threadIdx.x < 10) {
-        unsigned long long v = 0;
-        for (int w = 0; w < kThreads / 32; ++w) v += red[w][threadIdx.x];
-        if (v) atomicAdd(&scratch[threadIdx.x], v);
-    }
-}
-
-// one trie depth d (1 <= d <= k-1): count present nodes, propagate presence to depth d-1
-__global__ void __launch_bounds__(kThreads) finalize_depth_kernel(uint8_t *__restrict__ flags, int d, unsigned long long *__restrict__ scratch)
-{
-    const uint64_t groups = 1ull << (2 * (d - 1));
-    const uint32_t *lvl = reinterpret_cast<const uint32_t *>(flags + flags_offset(d));
-    unsigned long long nodes = 0;
-    for (uint64_t g = (uint64_t)blockIdx.x * kThreads + threadIdx.x; g < groups; g += (uint64_t)gridDim.x * kThreads) {
-        uint32_t v = lvl[g];
-        nodes += ((v & 0xffu) != 0) + ((v & 0xff00u) != 0) + ((v & 0xff0000u) != 0) + ((v & 0xff000000u) != 0);
-        if (d > 1 && v != 0) flags[flags_offset(d - 1) + g] = 1;
-    }
-    nodes = warp_sum(nodes);
-    if ((threadIdx.x & 31) == 0 && nodes) atomicAdd(&scratch[9], nodes);
-}
-
-// all trie depths d_top .. 1 in ONE block (4^8 = 65536 flags at most): the levels are tiny and strictly sequential
-__global__ void __launch_bounds__(1024) finalize_low_depths_kernel(uint8_t *__restrict__ flags, int d_top, unsigned long long *__restrict__ scratch)
-{
-    __shared__ unsigned long long s_nodes;
-    if (threadIdx.x == 0) s_nodes = 0;
-    __syncthreads();
-    unsigned long long nodes = 0;
-    for (int d = d_top; d >= 1; --d) {
-        const uint32_t groups = 1u << (2 * (d - 1));
-        const uint32_t *lvl = reinterpret_cast<const uint32_t *>(flags + flags_offset(d));
-        for (uint32_t g = threadIdx.x; g < groups; g += 1024) {
-            const uint32_t v = lvl[g];
-            nodes += ((v & 0xffu) != 0) + ((v & 0xff00u) != 0) + ((v & 0xff0000u) != 0) + ((v & 0xff000000u) != 0);
-            if (d > 1 && v != 0) flags[flags_offset(d - 1) + g] = 1;
-        }
-        __syncthreads();  // level d-1 is complete before it is read
-    }
-    nodes = warp_sum(nodes);
-    if ((threadIdx.x & 31) == 0 && nodes) atomicAdd(&s_nodes, nodes);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_nodes) atomicAdd(&scratch[9], s_nodes);
-}
-
-__global__ void finalize_counts_kernel(const unsigned long long *__restrict__ scratch, const fkb_partials *__restrict__ P,
-                                       uint64_t stream_bytes, fkb_counts *__restrict__ out)
-{
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    unsigned long long scratch[10];
+    for (int i = 0; i < 10; ++i) scratch[i] = __ldcg(scratch_g + i);  // written by atomics (some by this very block): read at L2
     fkb_counts c;
     c.n_kmers = scratch[0];
     c.base_total = 0;
@@ -301,6 +235,74 @@ __global__ void finalize_counts_kernel(const unsigned long long *__restrict__ sc
     c.rollover = (worst_visits >= (1ull << 32)) || (scratch[0] != P->n_windows);
     c.valid_bases = P->valid_bases;
     *out = c;
+}
+
+template <bool LEAF>
+__global__ void __launch_bounds__(kThreads) finalize_levels_kernel(const uint32_t *__restrict__ table, int k, int d_in, uint8_t *__restrict__ flags,
+                                                                   unsigned long long *__restrict__ scratch, int is_last,
+                                                                   const fkb_partials *__restrict__ P, uint64_t stream_bytes,
+                                                                   fkb_counts *__restrict__ out)
+{
+    const uint64_t n1 = 1ull << (2 * (d_in - 1));        // nodes at depth d_in-1 == groups of 4 siblings at depth d_in
+    const uint64_t n_round = (n1 + 31) & ~31ull;         // whole warps: every lane takes part in the ballots
+    const uint32_t lane = threadIdx.x & 31;
+    unsigned long long tot = 0, last[4] = {0, 0, 0, 0}, first[4] = {0, 0, 0, 0}, nodes = 0;
+    for (uint64_t g = (uint64_t)blockIdx.x * kThreads + threadIdx.x; g < n_round; g += (uint64_t)gridDim.x * kThreads) {
+        const bool in = g < n1;
+        uint32_t children = 0;  // present children of node g
+        if (in) {
+            if constexpr (LEAF) {
+                const uint4 v = reinterpret_cast<const uint4 *>(table)[g];
+                const unsigned long long sum = (unsigned long long)v.x + v.y + v.z + v.w;
+                tot += sum;
+                last[0] += v.x; last[1] += v.y; last[2] += v.z; last[3] += v.w;
+                if (k == 1) {
+                    first[0] += v.x; first[1] += v.y; first[2] += v.z; first[3] += v.w;
+                } else {
+                    const uint32_t fb = (uint32_t)(g >> (2 * (k - 2)));
+                    first[0] += (fb == 0) ? sum : 0; first[1] += (fb == 1) ? sum : 0;
+                    first[2] += (fb == 2) ? sum : 0; first[3] += (fb == 3) ? sum : 0;
+                }
+                children = (v.x != 0) + (v.y != 0) + (v.z != 0) + (v.w != 0);
+            } else {
+                const uint32_t v = reinterpret_cast<const uint32_t *>(flags + flags_offset(d_in))[g];
+                children = ((v & 0xffu) != 0) + ((v & 0xff00u) != 0) + ((v & 0xff0000u) != 0) + ((v & 0xff000000u) != 0);
+            }
+        }
+        nodes += children;                                                       // depth d_in
+        if (d_in < 2) continue;                                                  // depth d_in-1 is the head
+        const bool p1 = in && (children != 0 || flags[flags_offset(d_in - 1) + g] != 0);
+        nodes += p1;                                                             // depth d_in-1
+        const uint32_t m1 = __ballot_sync(0xffffffffu, p1);
+        if (d_in < 3) continue;
+        const uint64_t g2 = ((g - lane) >> 2) + lane;                            // lanes 0..7: the warp's 8 nodes at depth d_in-2
+        const bool p2 = lane < 8 && g2 < (n1 >> 2) && (((m1 >> (4 * lane)) & 0xFu) != 0 || flags[flags_offset(d_in - 2) + g2] != 0);
+        nodes += p2;                                                             // depth d_in-2
+        const uint32_t m2 = __ballot_sync(0xffffffffu, p2);
+        if (d_in < 4) continue;
+        const uint64_t g3 = ((g - lane) >> 4) + lane;                            // lanes 0..1: the warp's 2 nodes at depth d_in-3
+        if (lane < 2 && g3 < (n1 >> 4) && ((m2 >> (4 * lane)) & 0xFu) != 0) flags[flags_offset(d_in - 3) + g3] = 1;  // next launch's input
+    }
+    // block-level reduction: one set of global atomics per CTA instead of per warp (they all hit the same 10 words)
+    constexpr int NV = LEAF ? 10 : 1;
+    unsigned long long vals[10] = {tot, last[0], last[1], last[2], last[3], first[0], first[1], first[2], first[3], nodes};
+    if constexpr (!LEAF) vals[0] = nodes;
+    __shared__ unsigned long long red[kThreads / 32][10];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) vals[i] = warp_sum(vals[i]);
+    if (lane == 0)
+        for (int i = 0; i < NV; ++i) red[threadIdx.x >> 5][i] = vals[i];
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        unsigned long long v = 0;
+        for (int w = 0; w < kThreads / 32; ++w) v += red[w][threadIdx.x];
+        if (v) atomicAdd(&scratch[LEAF ? threadIdx.x : 9], v);
+    }
+    if (is_last) {  // single block (<= 16 nodes): every earlier launch has completed, this block's own atomics are ordered by the barrier
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) finalize_counts(scratch, P, stream_bytes, out);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -439,19 +441,15 @@ cudaError_t launch_finalize(const LaunchInfo &li, int k, const uint32_t *d_table
 {
     cudaError_t e = cudaMemsetAsync(d_scratch, 0, sizeof(unsigned long long) * kFinalizeScratchWords, st);
     if (e != cudaSuccess) return e;
-    finalize_table_kernel<<<grid_for(1ull << (2 * (k - 1)), li.sm_count, 8), kThreads, 0, st>>>(d_table, k, d_flags, d_scratch);
-    if (launches) ++*launches;
-    int d = k - 1;
-    for (; d > 8; --d) {  // wide levels: one launch each
-        finalize_depth_kernel<<<grid_for(1ull << (2 * (d - 1)), li.sm_count, 8), kThreads, 0, st>>>(d_flags, d, d_scratch);
+    for (int d_in = k; d_in >= 1; d_in -= 3) {  // three trie levels per launch
+        const int is_last = d_in <= 3;          // <= 16 threads of work: one block, which also assembles fkb_counts
+        const int grid = grid_for(1ull << (2 * (d_in - 1)), li.sm_count, 8);
+        if (d_in == k)
+            finalize_levels_kernel<true><<<grid, kThreads, 0, st>>>(d_table, k, d_in, d_flags, d_scratch, is_last, d_partials, stream_bytes, d_counts);
+        else
+            finalize_levels_kernel<false><<<grid, kThreads, 0, st>>>(d_table, k, d_in, d_flags, d_scratch, is_last, d_partials, stream_bytes, d_counts);
         if (launches) ++*launches;
     }
-    if (d >= 1) {  // the remaining <= 8 levels in one block
-        finalize_low_depths_kernel<<<1, 1024, 0, st>>>(d_flags, d, d_scratch);
-        if (launches) ++*launches;
-    }
-    finalize_counts_kernel<<<1, 32, 0, st>>>(d_scratch, d_partials, stream_bytes, d_counts);
-    if (launches) ++*launches;
     return cudaGetLastError();
 }
 
