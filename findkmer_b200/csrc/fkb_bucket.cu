@@ -284,39 +284,44 @@ __device__ __noinline__ void red_kmers_of_word(uint32_t wcode, uint32_t *table_k
 // rare per-run events of one group (positions given as bits of 16-bit masks, first byte = bit 15).
 // ev[0..3] head_base, ev[4..7] short_first, ev[8] runs_ge_k: CTA-private counters in shared memory -- soft-masked /
 // N-rich genomes have millions of run boundaries, and global atomics on nine fixed addresses would serialise them.
-__device__ __noinline__ void group_events(uint32_t first_k, uint32_t shorts, uint32_t m32, uint32_t code_hi, uint32_t code_lo, int k,
-                                          uint8_t *flags, uint32_t *ev)
+// left: valid k-mers whose covering W-window is broken (run edges / range edges) -> one global red each on T_k.
+// Done by the WHOLE warp: `who` = ballot of the lanes whose group has
+// events.  Two source lanes are served per round (half-warp each); inside a half-warp lane j handles bit j of the three
+// 16-bit event masks, so a run start with its k-1 short positions costs one round instead of a 10-trip loop executed by one
+// lane while 31 wait (soft-masked / N-rich input has a run boundary in most warp iterations).
+__device__ __noinline__ void warp_group_events(uint32_t who, uint32_t left, uint32_t first_k, uint32_t shorts, uint32_t m32, uint32_t code_hi,
+                                               uint32_t code_lo, int k, uint8_t *flags, uint32_t *ev, uint32_t *table_k)
 {
+    const uint32_t lane = threadIdx.x & 31, b = lane & 15, half = lane >> 4;
     const uint32_t kmask = (k == 16) ? 0xffffffffu : ((1u << (2 * k)) - 1u);
-    while (first_k) {  // run length reached exactly k here: first k-1 bases of the window go to head_base (:1050-1056)
-        int b = 31 - __clz(first_k);
-        first_k &= ~(1u << b);
-        uint32_t kmer = __funnelshift_r(code_lo, code_hi, 2 * b) & kmask;
-        const uint32_t head = kmer >> 2;  // the first k-1 bases; composition by popcounts of the 2-bit digits
-        const uint32_t lo = head & 0x55555555u, hi = (head >> 1) & 0x55555555u;
-        const uint32_t cT = __popc(lo & hi), cG = __popc(hi & ~lo), cC = __popc(lo & ~hi), cA = (uint32_t)(k - 1) - cT - cG - cC;
-        if (cA) atomicAdd(&ev[0], cA);
-        if (cC) atomicAdd(&ev[1], cC);
-        if (cG) atomicAdd(&ev[2], cG);
-        if (cT) atomicAdd(&ev[3], cT);
-        atomicAdd(&ev[8], 1u);
-    }
-    while (shorts) {  // valid base whose run is still shorter than k: the reference inserts a short path (:1059-1062)
-        int b = 31 - __clz(shorts);
-        shorts &= ~(1u << b);
-        int run = __ffs(~(m32 >> b)) - 1;  // consecutive valid bytes ending here (1 .. k-1)
-        uint32_t prefix = __funnelshift_r(code_lo, code_hi, 2 * b) & ((1u << (2 * run)) - 1u);
-        flags[flags_offset(run) + prefix] = 1;
-        atomicAdd(&ev[4 + (prefix >> (2 * (run - 1)))], 1u);
-    }
-}
-
-__device__ __noinline__ void leftover_kmers(uint32_t left, uint32_t code_hi, uint32_t code_lo, uint32_t kmask, uint32_t *table_k)
-{
-    while (left) {  // k-mers whose covering W-window is broken (run edges / range edges): straight to T_k
-        int b = 31 - __clz(left);
-        left &= ~(1u << b);
-        red_add_u32(table_k + (__funnelshift_r(code_lo, code_hi, 2 * b) & kmask), 1u);
+    while (who) {
+        const int s0 = __ffs(who) - 1;
+        who &= who - 1;
+        const int s1 = who ? __ffs(who) - 1 : -1;
+        if (who) who &= who - 1;
+        const int src = half ? (s1 < 0 ? s0 : s1) : s0;
+        const bool live = !(half && s1 < 0);
+        const uint32_t L = __shfl_sync(0xffffffffu, left, src), F = __shfl_sync(0xffffffffu, first_k, src), Sh = __shfl_sync(0xffffffffu, shorts, src);
+        const uint32_t M = __shfl_sync(0xffffffffu, m32, src), Chi = __shfl_sync(0xffffffffu, code_hi, src), Clo = __shfl_sync(0xffffffffu, code_lo, src);
+        if (!live) continue;
+        const uint32_t win = __funnelshift_r(Clo, Chi, 2 * b);  // the 16 bases that end at bit b of the group (first byte = bit 15)
+        if ((L >> b) & 1u) red_add_u32(table_k + (win & kmask), 1u);  // a k-mer whose covering W-window is broken: straight to T_k
+        if ((F >> b) & 1u) {  // run length reached exactly k here: first k-1 bases of the window go to head_base (:1050-1056)
+            const uint32_t head = (win & kmask) >> 2;
+            const uint32_t lo = head & 0x55555555u, hi = (head >> 1) & 0x55555555u;
+            const uint32_t cT = __popc(lo & hi), cG = __popc(hi & ~lo), cC = __popc(lo & ~hi), cA = (uint32_t)(k - 1) - cT - cG - cC;
+            if (cA) atomicAdd(&ev[0], cA);
+            if (cC) atomicAdd(&ev[1], cC);
+            if (cG) atomicAdd(&ev[2], cG);
+            if (cT) atomicAdd(&ev[3], cT);
+            atomicAdd(&ev[8], 1u);
+        }
+        if ((Sh >> b) & 1u) {  // valid base whose run is still shorter than k: the reference inserts a short path (:1059-1062)
+            const int run = __ffs(~(M >> b)) - 1;  // consecutive valid bytes ending here (1 .. k-1)
+            const uint32_t prefix = win & ((1u << (2 * run)) - 1u);
+            flags[flags_offset(run) + prefix] = 1;
+            atomicAdd(&ev[4 + (prefix >> (2 * (run - 1)))], 1u);
+        }
     }
 }
 
@@ -390,7 +395,6 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
     constexpr int K = kW - S + 1;
     constexpr int CH = 16 * S;                     // bytes per lane per iteration: exactly 16 items
     constexpr int J = S - 1;
-    constexpr uint32_t KMASK = (1u << (2 * K)) - 1u;
     constexpr uint64_t WSPAN = 32ull * CH;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     P1Smem &sm = *reinterpret_cast<P1Smem *>(smem_raw);
@@ -502,12 +506,10 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
 #pragma unroll
                     for (int d = 1; d <= J; ++d) cov |= (E << d);
                     const uint32_t left = rk & ~(cov >> 16);
-                    if (left) leftover_kmers(left, grp[g - 1].code, grp[g].code, KMASK, table_k);
-                    if (m != 0xFFFFFFFFu) {
-                        const uint32_t first_k = rk & ~(m >> K) & 0xFFFFu;
-                        const uint32_t shorts = grp[g].valid & ~rk;
-                        if (first_k | shorts) group_events(first_k, shorts, m, grp[g - 1].code, grp[g].code, K, flags, sm.ev);
-                    }
+                    const uint32_t first_k = rk & ~(m >> K) & 0xFFFFu;   // empty when m is all ones
+                    const uint32_t shorts = grp[g].valid & ~rk;
+                    const uint32_t who = __ballot_sync(0xffffffffu, (left | first_k | shorts) != 0);
+                    if (who) warp_group_events(who, left, first_k, shorts, m, grp[g - 1].code, grp[g].code, K, flags, sm.ev, table_k);
                 }
             }
 
