@@ -332,18 +332,13 @@ __device__ __noinline__ void warp_group_events(uint32_t who, uint32_t left, uint
 struct P1Smem {
     uint16_t stage[kNB * kStageCap];
     uint32_t cursor[kNB];  // items staged in the row
+    uint32_t junk[32];     // directly behind cursor[]: one junk cursor per lane, the target of the slot atomic of an item that is NOT emitted
     uint32_t goff[kNB];    // items already appended to this CTA's region of the bucket (multiple of 8 until the end)
     uint32_t ev[16];       // per-run event counters (see group_events), flushed to the partials once per tile
 };
 
-// predicated shared-memory atomic / store on 32-bit shared addresses: no branches, so the 8 atomics of a batch issue
+// shared-memory atomic / predicated store on 32-bit shared addresses: no branches, so the 8 atomics of a batch issue
 // back to back and their latencies overlap (the compiler otherwise serialises `if (p) pos = atomicAdd(...)` chains)
-__device__ __forceinline__ uint32_t atoms_inc_if(uint32_t saddr, uint32_t pred, uint32_t if_not)
-{
-    uint32_t old = if_not;
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p atom.shared.add.u32 %0, [%1], 1;\n\t}" : "+r"(old) : "r"(saddr), "r"(pred) : "memory");
-    return old;
-}
 // a * b + c as ONE integer multiply-add (FMA pipe); written in PTX so that the address arithmetic of the staging code is not
 // re-associated into shift + mask pairs on the ALU pipe, which is the busier one in pass 1
 __device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c)
@@ -543,7 +538,14 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
                         }
                         const uint32_t ca = mad_u32(bk[n - 8 * h], 4u, cursor_sa);  // &cursor[bucket]
                         if constexpr (ALL) pos[n - 8 * h] = atoms_inc(ca);
-                        else pos[n - 8 * h] = atoms_inc_if(ca, emit[g] & (1u << (15 - i)), 0xFFFFFFFFu);  // not emitted: no slot
+                        else {
+                            // An item that is not emitted still performs its atomic -- on this lane's junk cursor -- so that the 8 atomics
+                            // of the batch stay unconditional and issue back to back (ptxas turns a predicated atomic that returns a value
+                            // into a branch, which serialises the batch on soft-masked / N-rich input).
+                            const uint32_t e = emit[g] & (1u << (15 - i));
+                            const uint32_t ps = atoms_inc(e ? ca : cursor_sa + 4u * (uint32_t)(kNB + lane));
+                            pos[n - 8 * h] = e ? ps : 0xFFFFFFFFu;  // not emitted: no slot
+                        }
                     }
 #pragma unroll
                     for (int g = 0; g < S; ++g)
