@@ -5,8 +5,7 @@
         --log-file gpurun_out/traffic.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline
     python profiles/tools/traffic_summary.py gpurun_out/traffic.csv > profiles/rNN_traffic_k11.json
 
-Takes the kernels of the LAST step (from the last count_direct/bucketize launch that starts a step to the last
-finalize_counts_kernel) and prints the JSON bench.py reads for `roofline.traffic`."""
+Takes the kernels of the LAST step (from the last count_direct_kernel launch, which starts a step, to the end of the capture) and prints the JSON bench.py reads for `roofline.traffic`."""
 import csv
 import json
 import re
@@ -22,12 +21,11 @@ def main():
         d["unit_" + r[12]] = r[13]
     ids = sorted(launches)
     names = [launches[i]["kernel"] for i in ids]
-    ends = [i for i, n in zip(ids, names) if "finalize_counts_kernel" in n]
-    if not ends:
-        sys.exit("no finalize_counts_kernel launch in the capture")
-    end = ends[-1]
-    prev_end = ends[-2] if len(ends) > 1 else -1
-    step = [i for i in ids if prev_end < i <= end and "fkb" in launches[i]["kernel"] or (prev_end < i <= end and "unnamed" in launches[i]["kernel"])]
+    # a step = [count_direct_kernel (the edge slivers), bucketize, count_buckets, (fold levels), finalize levels]: take the last one
+    starts = [i for i, n in zip(ids, names) if "count_direct_kernel" in n]
+    if not starts:
+        sys.exit("no count_direct_kernel launch in the capture")
+    step = [i for i in ids if i >= starts[-1] and ("fkb" in launches[i]["kernel"] or "unnamed" in launches[i]["kernel"])]
     kernels, total = [], 0
     for i in step:
         d = launches[i]
