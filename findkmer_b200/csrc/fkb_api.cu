@@ -107,6 +107,10 @@ int ensure_bucket_scratch(fkb_context *ctx, int k, uint64_t range_bytes)
     const uint64_t n_seg = n_cta * (uint64_t)fkb::bucket_segments_per_sm();
     uint64_t cap = (4 * (items / (nb * n_seg)) + 64 + 7) & ~7ull;
     if (cap > 0x7FFFFFF8ull) cap = 0x7FFFFFF8ull;
+    if (!fkb::bucket_folds_in_shared(k)) {  // k <= 8 only: the 16-bit 13-mer table (128 MiB) and the fold levels
+        if (!ctx->bucket.table_w) FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.table_w, fkb::bucket_table_w_bytes()));
+        if (!ctx->bucket.fold) FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.fold, fkb::bucket_fold_bytes()));
+    }
     if (ctx->bucket.gbuf && ctx->bucket.cap_cb >= cap) return FKB_OK;
     if (ctx->bucket.gbuf) cudaFree(ctx->bucket.gbuf);
     ctx->bucket.gbuf = nullptr;
@@ -116,8 +120,6 @@ int ensure_bucket_scratch(fkb_context *ctx, int k, uint64_t range_bytes)
         FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.gcount, nb * n_seg * sizeof(uint32_t)));
         FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.work, 64));
     }
-    if (!ctx->bucket.table_w) FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.table_w, fkb::bucket_table_w_bytes()));
-    if (!ctx->bucket.fold) FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.fold, fkb::bucket_fold_bytes()));
     FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.gbuf, nb * n_seg * cap * sizeof(uint16_t)));
     ctx->bucket.cap_cb = (uint32_t)cap;
     return FKB_OK;

@@ -977,6 +977,7 @@ size_t bucket_fold_bytes()
     return words * sizeof(uint32_t);
 }
 int bucket_count() { return kNB; }
+bool bucket_folds_in_shared(int k) { const int S = bucket_stride_for(k); return S >= 1 && S <= kCoreMaxS && S <= 5; }  // ItemFmt<S>::kCore
 int bucket_segments_per_sm() { return FKB_P1_MINBLOCKS; }
 
 cudaError_t launch_count_bucketed(const LaunchInfo &li, const BucketScratch &bs, const uint8_t *d_stream, uint64_t lo, uint64_t hi, int k,

@@ -410,6 +410,35 @@ def test_full_size_properties(counter):
     torch.cuda.empty_cache()
 
 
+def test_large_soft_masked_bucketed_equals_direct(counter):
+    """1 Gbp of the config-5 shape (N runs + soft-masked runs: a run boundary in most warp iterations, so the general path of
+    pass 1 -- masks, warp-cooperative run events, junk-cursor atomics, re-read on leaving a clean stretch -- carries the load):
+    the bucketed path and the direct kernel must agree bin for bin and scalar for scalar, for a core-bucket k and a top-bit k"""
+    import torch
+    from findkmer_b200 import synth
+    lay = synth.config5(n_bases=int(os.environ.get("FKB_TEST_MASKED_BASES", 1_000_000_000))).stripped()
+    d = counter.synth_fasta_device(lay)
+    n = d.numel()
+    for k in (11, 8):
+        acc = counter.new_accumulators(k)
+        counter.count_stream_device(d, k, acc)
+        auto = counter.finalize_device(acc, n)
+        counter.set_variant(1)
+        try:
+            acc2 = counter.new_accumulators(k)
+            counter.count_stream_device(d, k, acc2)
+            direct = counter.finalize_device(acc2, n)
+        finally:
+            counter.set_variant(0)
+        assert np.array_equal(auto.table, direct.table)
+        assert (auto.n_kmers, auto.base_total, auto.base_count, auto.node_count, auto.unknown_chars, auto.valid_bases, auto.runs_ge_k) == \
+               (direct.n_kmers, direct.base_total, direct.base_count, direct.node_count, direct.unknown_chars, direct.valid_bases, direct.runs_ge_k)
+        assert auto.n_kmers == int(auto.table.sum(dtype=np.uint64)) and 0 < auto.unknown_chars < n
+        del acc, acc2
+    del d
+    torch.cuda.empty_cache()
+
+
 # ---- the drop-in program against the untouched reference binary ---------------------------------------------
 def test_cli_binary_is_a_drop_in(harness, tmp_path):
     """findkmer_b200/bin/findKmer vs oracle/_ref/findKmer: same flags, same output file names, identical bytes"""
