@@ -400,7 +400,7 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
     if (threadIdx.x < 16) sm.ev[threadIdx.x] = 0;
     __syncthreads();
 
-    // this warp's contiguous share of the interior (the host keeps n_witers below 2^32: launch_count_bucketed)
+    // this warp's contiguous share of the interior (the host keeps n_witers below 2^32: run_bucketed)
     const uint64_t n_warps = (uint64_t)gridDim.x * kP1Warps, gw = (uint64_t)blockIdx.x * kP1Warps + warp;
     const uint64_t q = n_witers / n_warps, rem = n_witers % n_warps;
     const uint32_t my_iters = (uint32_t)(q + (gw < rem ? 1 : 0));
@@ -948,6 +948,7 @@ cudaError_t run_bucketed(const LaunchInfo &li, const BucketScratch &bs, const ui
     }
     const uint64_t wspan = 32ull * 16 * S;
     const uint64_t n_witers = (hi - lo) / wspan;
+    if (n_witers >> 32) return cudaErrorInvalidValue;  // the kernel counts a warp's iterations in 32 bits (a range of >= 2 TiB: not on this device)
     cudaError_t e = cudaMemsetAsync(bs.work, 0, 16, st);
     if (e != cudaSuccess) return e;
     bucketize_kernel<S><<<bs.n_cta * FKB_P1_MINBLOCKS, P1Cfg<S>::kThreads, sizeof(P1Smem), st>>>(d_stream, lo, n_witers, bs.gbuf, bs.cap_cb, bs.gcount, d_table, d_flags, d_partials);
