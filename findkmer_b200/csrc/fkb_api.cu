@@ -101,7 +101,7 @@ int ensure_bucket_scratch(fkb_context *ctx, int k, uint64_t range_bytes)
 {
     const int S = fkb::bucket_stride_for(k);
     if (!S || ctx->forced_variant == fkb::VARIANT_DIRECT) return FKB_OK;
-    if (range_bytes < (64ull << 20) && ctx->forced_variant != fkb::VARIANT_BUCKET) return FKB_OK;  // the direct kernel will run
+    if (range_bytes < fkb::bucket_min_bytes(k) && ctx->forced_variant != fkb::VARIANT_BUCKET) return FKB_OK;  // the direct kernel will run
     const uint64_t items = range_bytes / S + 1;
     const uint64_t nb = (uint64_t)fkb::bucket_count(), n_cta = (uint64_t)ctx->sm_count;
     const uint64_t n_seg = n_cta * (uint64_t)fkb::bucket_segments_per_sm();

@@ -411,9 +411,18 @@ static cudaError_t launch_direct(const LaunchInfo &li, const uint8_t *d_stream, 
     return cudaGetLastError();
 }
 
-// below this many interior bytes the fixed costs of the bucketed path (1024 sub-table write-outs + the fold) lose
-// against one red per window
-constexpr uint64_t kBucketMinBytes = 96ull << 20;
+// Below this many interior bytes the fixed costs of the bucketed path (1024 buckets to zero / fold / write out, fold kernels
+// for k <= 8) lose against one red per window.  Measured crossovers on B200 (profiles/r01_crossover_direct_bucketed.txt):
+// the direct kernel runs at ~40 Gbases/s at k = 6 (same-address contention in L2) and ~180 Gbases/s from k = 9 up.
+uint64_t bucket_min_bytes(int k)
+{
+    if (k <= 6) return 12ull << 20;
+    if (k == 7) return 24ull << 20;
+    if (k == 8) return 44ull << 20;
+    if (k == 9) return 36ull << 20;
+    if (k == 10) return 30ull << 20;
+    return 22ull << 20;
+}
 
 cudaError_t launch_count(const LaunchInfo &li, const uint8_t *d_stream, uint64_t begin, uint64_t end, int k, uint32_t *d_table,
                          uint8_t *d_flags, fkb_partials *d_partials, cudaStream_t st, int *launches)
@@ -426,7 +435,7 @@ cudaError_t launch_count(const LaunchInfo &li, const uint8_t *d_stream, uint64_t
         // interior [lo, hi): whole units, aligned in absolute stream coordinates, 16 readable bytes on both sides
         lo = (begin + 16 + unit - 1) / unit * unit;
         hi = end >= 16 ? (end - 16) / unit * unit : 0;
-        const uint64_t min_bytes = li.variant == VARIANT_BUCKET ? unit : kBucketMinBytes;
+        const uint64_t min_bytes = li.variant == VARIANT_BUCKET ? unit : bucket_min_bytes(k);
         bucket = hi > lo && hi - lo >= min_bytes;
     }
     if (!bucket) return launch_direct(li, d_stream, begin, end, 0, 0, k, d_table, d_flags, d_partials, st, launches);

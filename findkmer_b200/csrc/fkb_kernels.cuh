@@ -35,6 +35,7 @@ uint64_t bucket_unit_bytes(int k);   // interior granularity of the bucketed pat
 size_t bucket_table_w_bytes();
 size_t bucket_fold_bytes();
 int bucket_count();
+uint64_t bucket_min_bytes(int k);    // interior bytes from which the bucketed path beats the direct kernel (measured crossovers)
 bool bucket_folds_in_shared(int k);  // core buckets (k >= 9): pass 2 folds in shared memory, no W-mer table / fold scratch in HBM
 int bucket_segments_per_sm();  // pass-1 CTAs per SM (each owns one segment per bucket)
 cudaError_t launch_count_bucketed(const LaunchInfo &li, const BucketScratch &bs, const uint8_t *d_stream, uint64_t lo, uint64_t hi, int k,
