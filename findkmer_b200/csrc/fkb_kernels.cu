@@ -111,7 +111,8 @@ __device__ __noinline__ void rare_event(uint32_t kmer, int run, int k, uint8_t *
     }
 }
 
-template <bool EDGE>
+// PRIV: `table` is the CTA's private copy of the table in shared memory (k <= 7), otherwise the global table
+template <bool EDGE, bool PRIV>
 __device__ __forceinline__ void step_owned(Scan &s, uint32_t c, uint32_t mask, int k, uint32_t *table, uint8_t *flags,
                                            uint32_t *P, Tally &t, uint64_t pos, uint64_t begin, uint64_t end)
 {
@@ -124,34 +125,45 @@ __device__ __forceinline__ void step_owned(Scan &s, uint32_t c, uint32_t mask, i
         t.valid += valid;
         t.unknown += (!valid && c != 'N' && c != '>');
         if (s.run >= k) {
-            red_add_u32(table + s.kmer, 1u);
+            if constexpr (PRIV) atomicAdd(table + s.kmer, 1u);
+            else red_add_u32(table + s.kmer, 1u);
             t.windows++;
         }
         if ((unsigned)(s.run - 1) < (unsigned)k) rare_event(s.kmer, s.run, k, flags, P);
     }
 }
 
-template <bool EDGE>
+template <bool EDGE, bool PRIV>
 __device__ __forceinline__ void scan_word(Scan &s, uint32_t w, uint32_t mask, int k, uint32_t *table, uint8_t *flags,
                                           uint32_t *P, Tally &t, uint64_t pos, uint64_t begin, uint64_t end)
 {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) step_owned<EDGE>(s, (w >> (8 * j)) & 0xffu, mask, k, table, flags, P, t, pos + j, begin, end);
+    for (int j = 0; j < 4; ++j) step_owned<EDGE, PRIV>(s, (w >> (8 * j)) & 0xffu, mask, k, table, flags, P, t, pos + j, begin, end);
 }
 
 // ------------------------------------------------------------------------------------------------
 // VARIANT_DIRECT: fused encode + count, one red.global.add.u32 per window.
 // The 4^k table (16 MiB at k = 11) is L2-resident; the atomics never reach HBM.
+// PRIV (k <= 7, ranges of some length): the 4^k counters (<= 64 KiB) are privatised per CTA in shared memory -- with 4096 or
+// 16384 bins the global reds of a whole GPU pile up on the same L2 lines (40 Gbases/s at k = 6) -- and added to the global
+// table once at the end.
 // ------------------------------------------------------------------------------------------------
 // A second range [begin2, end2) may ride along (blockIdx.y == 1): the two edge slivers around a bucketed interior.
+template <bool PRIV>
 __global__ void __launch_bounds__(kThreads) count_direct_kernel(const uint8_t *__restrict__ s, uint64_t begin, uint64_t end, uint64_t begin2,
-                                                                uint64_t end2, int k, uint32_t *__restrict__ table, uint8_t *__restrict__ flags,
+                                                                uint64_t end2, int k, uint32_t *__restrict__ gtable, uint8_t *__restrict__ flags,
                                                                 fkb_partials *__restrict__ P)
 {
     if (blockIdx.y == 1) { begin = begin2; end = end2; }
     if (end <= begin) return;
+    extern __shared__ __align__(16) uint32_t priv_table[];
     __shared__ uint32_t ev[16];
     if (threadIdx.x < 16) ev[threadIdx.x] = 0;
+    uint32_t *table = gtable;
+    if constexpr (PRIV) {
+        table = priv_table;
+        for (uint32_t i = threadIdx.x; i < (1u << (2 * k)); i += kThreads) priv_table[i] = 0;
+    }
     __syncthreads();
     const uint32_t mask = (k == 16) ? 0xffffffffu : ((1u << (2 * k)) - 1u);
     const uint64_t base = begin & ~15ull;                      // chunks are 16-byte aligned in the stream
@@ -172,7 +184,7 @@ __global__ void __launch_bounds__(kThreads) count_direct_kernel(const uint8_t *_
                 for (int j = 0; j < 4; ++j) step_context(sc, (hw[i] >> (8 * j)) & 0xffu, mask);
             const uint32_t w[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
 #pragma unroll
-            for (int i = 0; i < 16; ++i) scan_word<false>(sc, w[i], mask, k, table, flags, ev, t, p0 + 4 * i, begin, end);
+            for (int i = 0; i < 16; ++i) scan_word<false, PRIV>(sc, w[i], mask, k, table, flags, ev, t, p0 + 4 * i, begin, end);
         } else {
             uint4 h = load16_guarded(s, (int64_t)p0 - 16, end);
             const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
@@ -181,11 +193,17 @@ __global__ void __launch_bounds__(kThreads) count_direct_kernel(const uint8_t *_
             for (int g = 0; g < 4; ++g) {
                 uint4 v = load16_guarded(s, (int64_t)(p0 + 16 * g), end);
                 const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                for (int i = 0; i < 4; ++i) scan_word<true>(sc, w[i], mask, k, table, flags, ev, t, p0 + 16 * g + 4 * i, begin, end);
+                for (int i = 0; i < 4; ++i) scan_word<true, PRIV>(sc, w[i], mask, k, table, flags, ev, t, p0 + 16 * g + 4 * i, begin, end);
             }
         }
     }
     __syncthreads();
+    if constexpr (PRIV) {
+        for (uint32_t i = threadIdx.x; i < (1u << (2 * k)); i += kThreads) {
+            const uint32_t v = priv_table[i];
+            if (v) red_add_u32(gtable + i, v);
+        }
+    }
     if (threadIdx.x < 9 && ev[threadIdx.x]) {
         unsigned long long *dst = threadIdx.x < 4 ? &P->head_base[threadIdx.x] : (threadIdx.x < 8 ? &P->short_first[threadIdx.x - 4] : &P->runs_ge_k);
         atomicAdd(dst, (unsigned long long)ev[threadIdx.x]);
@@ -405,19 +423,29 @@ static cudaError_t launch_direct(const LaunchInfo &li, const uint8_t *d_stream, 
     const uint64_t len1 = end > begin ? end - (begin & ~15ull) : 0, len2 = end2 > begin2 ? end2 - (begin2 & ~15ull) : 0;
     const uint64_t longest = len1 > len2 ? len1 : len2;
     if (!longest) return cudaSuccess;
-    dim3 grid((unsigned)grid_for((longest + kChunk - 1) / kChunk, li.sm_count, 8), len2 ? 2 : 1);
-    count_direct_kernel<<<grid, kThreads, 0, st>>>(d_stream, begin, end, begin2, end2, k, d_table, d_flags, d_partials);
+    if (k <= 7 && longest >= (256u << 10)) {  // private counters pay from a few hundred KiB on (every CTA adds its 4^k bins at the end)
+        if (k == 7) {  // 64 KiB of dynamic shared memory needs the opt-in (per device, so not cached in a static)
+            cudaError_t e = cudaFuncSetAttribute(count_direct_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            if (e != cudaSuccess) return e;
+        }
+        dim3 grid((unsigned)grid_for((longest + kChunk - 1) / kChunk, li.sm_count, k == 7 ? 2 : 4), len2 ? 2 : 1);
+        count_direct_kernel<true><<<grid, kThreads, sizeof(uint32_t) << (2 * k), st>>>(d_stream, begin, end, begin2, end2, k, d_table, d_flags, d_partials);
+    } else {
+        dim3 grid((unsigned)grid_for((longest + kChunk - 1) / kChunk, li.sm_count, 8), len2 ? 2 : 1);
+        count_direct_kernel<false><<<grid, kThreads, 0, st>>>(d_stream, begin, end, begin2, end2, k, d_table, d_flags, d_partials);
+    }
     if (launches) ++*launches;
     return cudaGetLastError();
 }
 
 // Below this many interior bytes the fixed costs of the bucketed path (1024 buckets to zero / fold / write out, fold kernels
 // for k <= 8) lose against one red per window.  Measured crossovers on B200 (profiles/r01_crossover_direct_bucketed.txt):
-// the direct kernel runs at ~40 Gbases/s at k = 6 (same-address contention in L2) and ~180 Gbases/s from k = 9 up.
+// the direct kernel runs at ~180 Gbases/s from k = 9 up (one global red per window) and, with its counters privatised in shared
+// memory, at ~430 / ~340 Gbases/s at k = 6 / 7.
 uint64_t bucket_min_bytes(int k)
 {
-    if (k <= 6) return 12ull << 20;
-    if (k == 7) return 24ull << 20;
+    if (k <= 6) return 150ull << 20;
+    if (k == 7) return 110ull << 20;
     if (k == 8) return 44ull << 20;
     if (k == 9) return 36ull << 20;
     if (k == 10) return 30ull << 20;
