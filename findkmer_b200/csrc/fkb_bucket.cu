@@ -54,10 +54,6 @@ constexpr int kStageCap = FKB_STAGE_CAP;       // staged items per bucket (13 ch
 #ifndef FKB_P1_THREADS_HI
 #define FKB_P1_THREADS_HI 448  // measured best at S = 6
 #endif
-#ifndef FKB_RED_SLOTS
-#define FKB_RED_SLOTS 0u  // bit n set: slot n of every chunk bypasses the routing and goes to T_k with S global reds.  MEASURED NEGATIVE:
-                          // 1 slot of 16 already costs +10 % (a scattered global red occupies the LSU ~10x longer than a shared atomic)
-#endif
 #ifndef FKB_P2_THREADS
 #define FKB_P2_THREADS 1024
 #endif
@@ -114,32 +110,9 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v)
     return v;
 }
 
-// Logical right shift by a constant.  The hot loops are bound by the ALU pipe (LOP3/SHF, ~70 % busy) while the FMA pipe
-// idles (~9 %): with FKB_SHR_VIA_IMAD the shift is issued as IMAD.HI (x * 2^(32-n) >> 32) on the FMA pipe instead.
-#ifndef FKB_OVF_VIA_MAX
-#define FKB_OVF_VIA_MAX 0
-#endif
-#ifndef FKB_ENC_V3
-#define FKB_ENC_V3 1  // fast encode: validity accumulated over the lane's whole chunk (left shifts go to the FMA pipe), one test per iteration
-#endif
-#ifndef FKB_ITEMS_V2
-#define FKB_ITEMS_V2 1  // W-mer left-aligned in the funnel-shifted word: bucket = word >> 22 (no masks), addresses by IMAD
-#endif
-#ifndef FKB_P2_V2
-#define FKB_P2_V2 1  // pass 2: drain test reduced to one AND per item (bit 15 of the counter's old value)
-#endif
-#ifndef FKB_SHR_VIA_IMAD
-#define FKB_SHR_VIA_IMAD 0
-#endif
+// logical right shift by a constant (issuing it as IMAD.HI on the FMA pipe was measured: +2 %, not kept)
 template <int N>
-__device__ __forceinline__ uint32_t shr_c(uint32_t x)
-{
-#if FKB_SHR_VIA_IMAD
-    return __umulhi(x, 1u << (32 - N));
-#else
-    return x >> N;
-#endif
-}
+__device__ __forceinline__ uint32_t shr_c(uint32_t x) { return x >> N; }
 
 // ---- SIMD-in-register encode of 4 ASCII bytes (one 32-bit word, byte 0 = lowest address) ----------------
 // codes: 8 bits, byte 0's 2-bit code in bits 7..6 (A0 C1 G2 T3 = base2int, findKmer.cpp:569-576)
@@ -195,7 +168,7 @@ __device__ __forceinline__ Group pack_group(const uint4 &g, uint32_t &unknown)
     return r;
 }
 
-// ---- fast encode (FKB_ENC_V3): codes only; validity is ACCUMULATED over many words and tested once ----------------
+// ---- fast encode: codes only; validity is ACCUMULATED over many words and tested once ----------------
 // A byte is one of A,C,G,T  <=>  b7 b6 b5 b3 = 0 1 0 0,  b4 == q,  b0 == ~q  with q = b2 & ~b1 (see encode_word).
 // The two relations are evaluated at bit 4 of every byte from LEFT-shifted copies of the word (left shifts are IMAD.SHL on
 // the otherwise idle FMA pipe, and shifting up never drags a neighbour byte's bits into bit 4); the four constant bits go
@@ -756,11 +729,9 @@ count_buckets_kernel(const uint16_t *__restrict__ gbuf, uint32_t cap_cb, const u
         __syncthreads();
         const uint32_t b = s_bucket;
         if (b >= (uint32_t)kNB) break;
-        // Two 16-bit counters per word.  A counter is drained at 0x8000 (not at 0xFFFF) so that a carry can never
-        // cross into its neighbour, whatever the interleaving of the other threads' updates: the increment that
-        // sees 0x7FFF moves 32768 counts to T_k exactly and takes them out of the half again.
-        // Eight items (one 128-bit load) at a time, branch-free: 8 shared atomics back to back, then 8 checks.
-#if FKB_P2_V2
+        // Two 16-bit counters per word.  A counter is drained around 0x8000 (not at 0xFFFF) so that a carry can never
+        // cross into its neighbour, whatever the interleaving of the other threads' updates (fewer than 32768 increments
+        // can be in flight).  Eight items (one 128-bit load) at a time, branch-free: 8 shared atomics back to back, then 8 checks.
         // The drain is triggered by the increment that SEES 0x8000 (unique: the half then reads 0x8001 and the trigger takes
         // 32768 out again), so the hot test is one AND per item: bit 15 of the half in the old value.  Whoever sees a half
         // in 0x8001..0xFFFE while a drain is pending takes the slow path and finds nothing to do.
@@ -799,36 +770,6 @@ count_buckets_kernel(const uint16_t *__restrict__ gbuf, uint32_t cap_cb, const u
             const uint32_t half = hi_half ? (old >> 16) : (old & 0xFFFFu);
             if (half == 0x8000u) drain_counter<S>(word, hi_half, ItemFmt<S>::wmer(b, idx), table_k);
         };
-#else
-        auto add8 = [&](const uint4 &v) {
-            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-            uint32_t old[8], sh[8], ovf = 0;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const uint32_t idx = (e & 1) ? (w4[e >> 1] >> 16) : (w4[e >> 1] & 0xFFFFu);
-                sh[e] = (idx & 1u) << 4;                                      // 0 or 16: which half of the word
-                const uint32_t sa = sub_sa + ((idx << 1) & 0x3FFFCu);          // &sub[idx >> 1]
-                asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old[e]) : "r"(sa), "r"(1u << sh[e]) : "memory");
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) ovf |= (uint32_t)(((old[e] >> sh[e]) & 0xFFFFu) == 0x7FFFu) << e;
-            if (ovf) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e)
-                    if (ovf & (1u << e)) {
-                        const uint32_t idx = (e & 1) ? (w4[e >> 1] >> 16) : (w4[e >> 1] & 0xFFFFu);
-                        drain_counter<S>(sub + (idx >> 1), idx & 1u, ItemFmt<S>::wmer(b, idx), table_k);
-                    }
-            }
-        };
-        auto add_item = [&](uint32_t idx) {
-            const uint32_t hi_half = idx & 1u;
-            uint32_t *word = sub + (idx >> 1);
-            const uint32_t old = atomicAdd(word, hi_half ? 0x10000u : 1u);
-            const uint32_t half = hi_half ? (old >> 16) : (old & 0xFFFFu);
-            if (half == 0x7FFFu) drain_counter<S>(word, hi_half, ItemFmt<S>::wmer(b, idx), table_k);
-        };
-#endif
         for (;;) {
             uint32_t seg = 0;
             if (lane == 0) seg = atomicAdd(&s_next_seg, 1u);
