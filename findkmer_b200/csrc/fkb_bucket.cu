@@ -52,7 +52,7 @@ constexpr int kStageCap = FKB_STAGE_CAP;       // staged items per bucket (13 ch
 #define FKB_P1_THREADS_LO 512  // measured: 512 > 640 > 768 > 1024 at S = 3 (registers beat warps: 80-register builds spill)
 #endif
 #ifndef FKB_P1_THREADS_HI
-#define FKB_P1_THREADS_HI 448  // measured best at S = 6
+#define FKB_P1_THREADS_HI 448  // S = 4, 5
 #endif
 #ifndef FKB_P2_THREADS
 #define FKB_P2_THREADS 1024
@@ -61,7 +61,10 @@ constexpr int kTileItems = FKB_TILE_AVG * kNB;         // items a CTA stages bet
 constexpr int kP2Threads = FKB_P2_THREADS;
 
 // pass-1 CTA size (1 CTA per SM: the staging rows take 208 KiB), tuned on B200 with build.build_variant()
-template <int S> struct P1Cfg { static constexpr int kThreads = (S <= 3) ? FKB_P1_THREADS_LO : FKB_P1_THREADS_HI; };
+#ifndef FKB_P1_THREADS_XL
+#define FKB_P1_THREADS_XL 384  // S >= 6 (k <= 8): the pipeline state is 10*S registers; 384 threads may use 168 each (448/512: 128 -> spills): k = 6 -14 %, k = 7 -9 %
+#endif
+template <int S> struct P1Cfg { static constexpr int kThreads = (S <= 3) ? FKB_P1_THREADS_LO : (S <= 5 ? FKB_P1_THREADS_HI : FKB_P1_THREADS_XL); };
 
 // Staging rows are 208 bytes (13 chunks of 16 bytes) apart: 52 words == 20 banks, so consecutive rows start on 8
 // different bank offsets and a warp's stores (all rows fill at about the same rate) spread over all 32 banks, while
