@@ -19,6 +19,8 @@
 #include <string.h>
 
 #include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -121,9 +123,28 @@ struct CompositionTable {
 
 inline unsigned popc32(uint32_t x) { return (unsigned)__builtin_popcount(x); }
 
+// ", <count>, <z>" of a row depends only on (composition, count): z = (x - n*p) / sd (:839) with n*p and sd fixed per
+// composition.  A genome's counts cluster (Poisson around n/4^k on random sequence; a few hundred distinct values per
+// composition on real ones), so the two printf("%LE")-class conversions per row -- the bulk of the writer's time -- are
+// memoised in a direct-mapped cache per worker thread.  The text is produced by the same snprintf calls as before, so the
+// bytes cannot differ.
+struct TailEntry {
+    uint64_t key;   // (composition index << 32 | count) + 1; 0 = empty
+    uint8_t len;
+    char text[39];  // ", %d" + ", %LE"  (11 + 14 characters at most... kept generous)
+};
+struct TailCache {
+    static constexpr uint32_t kBits = 14;
+    std::vector<TailEntry> e;
+    TailCache() : e((size_t)1 << kBits) {
+        for (auto &x : e) x.key = 0;
+    }
+    TailEntry &slot(uint32_t comp, uint32_t freq) { return e[((comp * 0x9E3779B1u) ^ (freq * 0x85EBCA77u)) >> (32 - kBits)]; }
+};
+
 // format the rows of table[lo, hi) into out
 void format_slice(const uint32_t *table, uint64_t lo, uint64_t hi, int k, const CompositionTable &ct, int z_enable, long double z_thr,
-                  std::string &out, uint64_t &rows)
+                  std::string &out, uint64_t &rows, TailCache &cache)
 {
     static const char letters[4] = {'A', 'C', 'G', 'T'};
     const uint32_t lo_bits = 0x55555555u;
@@ -136,17 +157,29 @@ void format_slice(const uint32_t *table, uint64_t lo, uint64_t hi, int k, const 
         const uint32_t lo1 = c32 & lo_bits, hi1 = (c32 >> 1) & lo_bits;
         const unsigned cT = popc32(lo1 & hi1), cG = popc32(hi1 & ~lo1), cC = popc32(lo1 & ~hi1);
         const unsigned cA = (unsigned)k - cT - cG - cC;
-        const Composition &cp = ct.comps[((size_t)cA * (k + 1) + cC) * (k + 1) + cG];
+        const uint32_t comp = (uint32_t)(((size_t)cA * (k + 1) + cC) * (k + 1) + cG);
+        const Composition &cp = ct.comps[comp];
         unsigned long long x = freq;
-        long double z = (x - cp.mean) / cp.sd;  // (:839)
-        if (!(z_enable == 0 || (z_enable > 0 && fabsl(z) >= z_thr))) continue;  // (:852-854)
+        TailEntry &te = cache.slot(comp, freq);
+        const uint64_t key = (((uint64_t)comp << 32) | freq) + 1;
+        const bool hit = te.key == key;
+        if (z_enable != 0 || !hit) {
+            long double z = (x - cp.mean) / cp.sd;  // (:839)
+            if (!(z_enable == 0 || (z_enable > 0 && fabsl(z) >= z_thr))) continue;  // (:852-854)
+            if (!hit) {
+                int m = snprintf(te.text, sizeof te.text, ", %d", (int)freq);                        // (:872)  %d of an unsigned
+                if (cp.normal_ok) m += snprintf(te.text + m, sizeof te.text - (size_t)m, ", %LE", z);  // (:875-885)
+                te.len = (uint8_t)m;
+                te.key = key;
+            }
+        }
         int n = 0;
         row[n++] = '\n';
         for (int i = k - 1; i >= 0; --i) row[n++] = letters[(c32 >> (2 * i)) & 3u];
         memcpy(row + n, cp.text, (size_t)cp.text_len);
         n += cp.text_len;
-        n += snprintf(row + n, sizeof row - (size_t)n, ", %d", (int)freq);                    // (:872)  %d of an unsigned
-        if (cp.normal_ok) n += snprintf(row + n, sizeof row - (size_t)n, ", %LE", z);        // (:875-885)
+        memcpy(row + n, te.text, te.len);
+        n += te.len;
         out.append(row, (size_t)n);
         ++rows;
     }
@@ -167,37 +200,63 @@ extern "C" int fkb_write_histogram(FILE *csv_out, int k, const uint32_t *table, 
         unsigned hc = std::thread::hardware_concurrency();
         n_threads = hc ? (int)(hc > 32 ? 32 : hc) : 4;
     }
-    // slices small enough to bound memory (a k = 11 table is ~170 MB of text), written strictly in order
+    // Slices small enough to bound memory (a k = 11 table is ~250 MB of text), written strictly in order.  Workers format
+    // slices into a small ring of buffers (reused, so only the first lap page-faults); the calling thread writes slice s as
+    // soon as it is done and hands its buffer to slice s + ring.
     const uint64_t slice = entries < 65536 ? entries : 65536;
     const uint64_t n_slices = entries / slice;
     if ((uint64_t)n_threads > n_slices) n_threads = (int)n_slices;
-    const uint64_t wave = (uint64_t)n_threads * 4;
-    std::vector<std::string> bufs(wave);
-    std::vector<uint64_t> rows(wave);
-    uint64_t total_rows = 0;
-    for (uint64_t s0 = 0; s0 < n_slices; s0 += wave) {
-        const uint64_t s1 = s0 + wave < n_slices ? s0 + wave : n_slices;
-        std::atomic<uint64_t> next{s0};
-        auto worker = [&] {
-            for (;;) {
-                uint64_t s = next.fetch_add(1);
-                if (s >= s1) return;
-                std::string &b = bufs[s - s0];
-                b.clear();
-                rows[s - s0] = 0;
-                format_slice(table, s * slice, (s + 1) * slice, k, ct, z_threshold_enable, z_threshold, b, rows[s - s0]);
+    const uint64_t ring = (uint64_t)n_threads * 2;
+    std::vector<std::string> bufs(ring);
+    std::vector<uint64_t> rows(n_slices, 0);
+    std::vector<char> done(n_slices, 0);
+    std::vector<TailCache> caches((size_t)n_threads);  // one per worker
+    std::mutex mu;
+    std::condition_variable cv;
+    uint64_t next = 0, written = 0;
+    bool abort_all = false;
+    auto worker = [&](int t) {
+        for (;;) {
+            uint64_t s;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                s = next++;
+                if (s >= n_slices) return;
+                cv.wait(lk, [&] { return abort_all || s < written + ring; });  // the slice's buffer has been written out
+                if (abort_all) return;
             }
-        };
-        std::vector<std::thread> pool;
-        for (int t = 1; t < n_threads; ++t) pool.emplace_back(worker);
-        worker();
-        for (auto &th : pool) th.join();
-        for (uint64_t s = s0; s < s1; ++s) {
-            const std::string &b = bufs[s - s0];
-            if (!b.empty() && fwrite(b.data(), 1, b.size(), csv_out) != b.size()) return FKB_ERR_IO;
-            total_rows += rows[s - s0];
+            std::string &b = bufs[s % ring];
+            b.clear();
+            format_slice(table, s * slice, (s + 1) * slice, k, ct, z_threshold_enable, z_threshold, b, rows[s], caches[(size_t)t]);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                done[s] = 1;
+            }
+            cv.notify_all();
         }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; ++t) pool.emplace_back(worker, t);
+    uint64_t total_rows = 0;
+    int status = FKB_OK;
+    for (uint64_t s = 0; s < n_slices; ++s) {
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return done[s] != 0; });
+        }
+        const std::string &b = bufs[s % ring];
+        if (!b.empty() && fwrite(b.data(), 1, b.size(), csv_out) != b.size()) status = FKB_ERR_IO;
+        total_rows += rows[s];
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            written = s + 1;
+            if (status != FKB_OK) abort_all = true;
+        }
+        cv.notify_all();
+        if (status != FKB_OK) break;
     }
+    for (auto &th : pool) th.join();
+    if (status != FKB_OK) return status;
     if (rows_written) *rows_written = total_rows;
     return FKB_OK;
 }
