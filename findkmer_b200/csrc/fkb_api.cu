@@ -105,8 +105,11 @@ int ensure_bucket_scratch(fkb_context *ctx, int k, uint64_t range_bytes)
     const uint64_t items = range_bytes / S + 1;
     const uint64_t nb = (uint64_t)fkb::bucket_count(), n_cta = (uint64_t)ctx->sm_count;
     const uint64_t n_seg = n_cta * (uint64_t)fkb::bucket_segments_per_sm();
-    uint64_t cap = (4 * (items / (nb * n_seg)) + 64 + 7) & ~7ull;
-    if (cap > 0x7FFFFFF8ull) cap = 0x7FFFFFF8ull;
+    // front part: 4x the average fill (flushed 16-byte chunks); back part: as much again for items whose staging row was full
+    // (16.8 GB of the 180 GB for a 3.1 Gbp range at k = 11)
+    uint64_t cap_front = (4 * (items / (nb * n_seg)) + 64 + 7) & ~7ull;
+    if (cap_front > 0x3FFFFFF8ull) cap_front = 0x3FFFFFF8ull;
+    uint64_t cap = 2 * cap_front;
     if (!fkb::bucket_folds_in_shared(k)) {  // k <= 8 only: the 16-bit 13-mer table (128 MiB) and the fold levels
         if (!ctx->bucket.table_w) FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.table_w, fkb::bucket_table_w_bytes()));
         if (!ctx->bucket.fold) FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.fold, fkb::bucket_fold_bytes()));
@@ -117,11 +120,12 @@ int ensure_bucket_scratch(fkb_context *ctx, int k, uint64_t range_bytes)
     ctx->bucket.cap_cb = 0;
     ctx->bucket.n_cta = (int)n_cta;
     if (!ctx->bucket.gcount) {
-        FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.gcount, nb * n_seg * sizeof(uint32_t)));
-        FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.work, 64));
+        FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.gcount, 2 * nb * n_seg * sizeof(uint32_t)));
+        FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.work, 64 + nb * sizeof(uint32_t)));  // pass-2 work counter, then one item total per bucket
     }
     FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.gbuf, nb * n_seg * cap * sizeof(uint16_t)));
     ctx->bucket.cap_cb = (uint32_t)cap;
+    ctx->bucket.cap_front = (uint32_t)cap_front;
     return FKB_OK;
 }
 

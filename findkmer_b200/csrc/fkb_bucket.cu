@@ -309,7 +309,8 @@ struct P1Smem {
     uint16_t stage[kNB * kStageCap];
     uint32_t cursor[kNB];  // items staged in the row
     uint32_t junk[32];     // directly behind cursor[]: one junk cursor per lane, the target of the slot atomic of an item that is NOT emitted
-    uint32_t goff[kNB];    // items already appended to this CTA's region of the bucket (multiple of 8 until the end)
+    uint32_t goff[kNB];    // items already appended to the FRONT part of this CTA's region of the bucket (multiple of 8 until the end)
+    uint32_t gback[kNB];   // items written straight to the BACK part of the region because the staging row was full (skewed input)
     uint32_t ev[16];       // per-run event counters (see group_events), flushed to the partials once per tile
 };
 
@@ -357,8 +358,9 @@ __device__ __noinline__ void escape_chunk(uint32_t bucket, uint4 v, uint32_t *ta
 
 template <int S>
 __global__ void __launch_bounds__(P1Cfg<S>::kThreads, FKB_P1_MINBLOCKS)
-bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, uint16_t *__restrict__ gbuf, uint32_t cap_cb,
-                 uint32_t *__restrict__ gcount, uint32_t *__restrict__ table_k, uint8_t *__restrict__ flags, fkb_partials *__restrict__ P)
+bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, uint16_t *__restrict__ gbuf, uint32_t cap_cb, uint32_t cap_front,
+                 uint32_t *__restrict__ gcount, uint32_t *__restrict__ bucket_total, uint32_t *__restrict__ table_k, uint8_t *__restrict__ flags,
+                 fkb_partials *__restrict__ P)
 {
     static_assert(S >= 1 && S <= 8, "stride");
     constexpr int kP1Threads = P1Cfg<S>::kThreads, kP1Warps = kP1Threads / 32;
@@ -372,7 +374,7 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t cursor_sa = (uint32_t)__cvta_generic_to_shared(sm.cursor), stage_sa = (uint32_t)__cvta_generic_to_shared(sm.stage);
 
-    for (int b = threadIdx.x; b < kNB; b += kP1Threads) { sm.cursor[b] = 0; sm.goff[b] = 0; }
+    for (int b = threadIdx.x; b < kNB; b += kP1Threads) { sm.cursor[b] = 0; sm.goff[b] = 0; sm.gback[b] = 0; }
     if (threadIdx.x < 16) sm.ev[threadIdx.x] = 0;
     __syncthreads();
 
@@ -541,9 +543,22 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
                         sts16_if(sa, pay, ps < (uint32_t)kStageCap);
                         top = max(top, ps + 1u);
                     }
-                    if (top > (uint32_t)kStageCap) {  // some staging row is full (skewed input): record which slots
+                    if (top > (uint32_t)kStageCap) {
+                        // Some staging row is full (a bucket that is more popular than the tile size allows for: skewed base
+                        // composition, repeats).  The item goes straight to the BACK part of this CTA's region of the bucket:
+                        // one more shared atomic and a 2-byte global store instead of a staged slot.  Only when that part is
+                        // full too is the item escaped exactly with global reds (ovf).
 #pragma unroll
-                        for (int n = 0; n < 8; ++n) ovf |= (uint32_t)(pos[n] != 0xFFFFFFFFu && pos[n] >= (uint32_t)kStageCap) << (n + 8 * h);
+                        for (int n = 0; n < 8; ++n) {
+                            if (pos[n] != 0xFFFFFFFFu && pos[n] >= (uint32_t)kStageCap) {
+                                const uint32_t q = atomicAdd(&sm.gback[bk[n]], 1u);
+                                uint32_t pay;
+                                if constexpr (ItemFmt<S>::kCore) pay = (f[n] & ItemFmt<S>::rmask()) | ((f[n] >> 10) & ~ItemFmt<S>::rmask());
+                                else pay = f[n] >> 6;
+                                if (q < cap_cb - cap_front) my_gbuf[(uint64_t)bk[n] * gridDim.x * cap_cb + cap_front + q] = (uint16_t)pay;
+                                else ovf |= 1u << (n + 8 * h);
+                            }
+                        }
                     }
                 }
             };
@@ -584,7 +599,7 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
             uint32_t n_seg;  // gridDim.x, read here so that the flush's invariants do not occupy registers across the streaming loop
             asm volatile("mov.u32 %0, %%nctaid.x;" : "=r"(n_seg));
             const uint64_t bstride = (uint64_t)n_seg * cap_cb;
-            const uint32_t cap8 = cap_cb & ~7u;
+            const uint32_t cap8 = cap_front & ~7u;  // the flushed chunks fill the front part of the region
             for (uint32_t b0 = warp * 32; b0 < (uint32_t)kNB; b0 += kP1Warps * 32) {
                 const uint32_t bl = b0 + lane;
                 const uint32_t cnt = min(sm.cursor[bl], (uint32_t)kStageCap);
@@ -634,10 +649,13 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
         uint16_t *dst = my_gbuf + (uint64_t)b * gridDim.x * cap_cb;
         for (uint32_t i = 0; i < cnt; ++i) {
             const uint16_t item = sm.stage[stage_slot(b, i)];
-            if (off < cap_cb) dst[off++] = item;
+            if (off < cap_front) dst[off++] = item;
             else red_kmers_of_word<S>(ItemFmt<S>::wmer((uint32_t)b, item), table_k, 1u);
         }
-        gcount[(uint64_t)b * gridDim.x + blockIdx.x] = off;
+        gcount[2 * ((uint64_t)b * gridDim.x + blockIdx.x)] = off;                                          // front part: [0, off)
+        const uint32_t back = min(sm.gback[b], cap_cb - cap_front);
+        gcount[2 * ((uint64_t)b * gridDim.x + blockIdx.x) + 1] = back;                                     // back part: [cap_front, cap_front + back)
+        if (off + back) atomicAdd(&bucket_total[b], off + back);  // pass 2 takes the buckets largest first
     }
     t_windows += (unsigned long long)n_fast * (16 * S);
     t_valid += (unsigned long long)n_fast * (16 * S);
@@ -718,20 +736,40 @@ __device__ __noinline__ void drain_counter(uint32_t *word, uint32_t hi_half, uin
 
 template <int S>
 __global__ void __launch_bounds__(kP2Threads, 1)
-count_buckets_kernel(const uint16_t *__restrict__ gbuf, uint32_t cap_cb, const uint32_t *__restrict__ gcount, int n_seg,
+count_buckets_kernel(const uint16_t *__restrict__ gbuf, uint32_t cap_cb, uint32_t cap_front, const uint32_t *__restrict__ gcount, int n_seg,
                      uint16_t *__restrict__ table_w, uint32_t *__restrict__ table_k, uint32_t *__restrict__ work)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t *sub = reinterpret_cast<uint32_t *>(smem_raw);  // 32768 words = 65536 packed 16-bit counters
     __shared__ uint32_t s_bucket, s_next_seg;
+    __shared__ uint32_t s_total[kNB];
+    __shared__ uint16_t s_order[kNB];
     const int lane = threadIdx.x & 31;
     const uint32_t sub_sa = (uint32_t)__cvta_generic_to_shared(sub);
+    // Largest bucket first (every CTA sorts the 1024 bucket sizes for itself: 55 compare-exchange steps, ~2 us): real genomes
+    // load the buckets unevenly (base composition, repeats), and a bucket several times the average that is started last
+    // would be the tail of the kernel.
+    const uint32_t *bucket_total = work + 16;
+    for (int i = threadIdx.x; i < kNB; i += kP2Threads) { s_total[i] = bucket_total[i]; s_order[i] = (uint16_t)i; }
+    __syncthreads();
+    for (int k2 = 2; k2 <= kNB; k2 <<= 1)
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < kNB; i += kP2Threads) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const uint16_t a = s_order[i], c = s_order[ixj];
+                    const uint32_t ta = s_total[a], tc = s_total[c];
+                    if (((i & k2) == 0) ? (ta < tc) : (ta > tc)) { s_order[i] = c; s_order[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
     for (;;) {
         if (threadIdx.x == 0) { s_bucket = atomicAdd(work, 1u); s_next_seg = 0; }
         for (int i = threadIdx.x; i < 32768 / 4; i += kP2Threads) reinterpret_cast<uint4 *>(sub)[i] = make_uint4(0, 0, 0, 0);
         __syncthreads();
-        const uint32_t b = s_bucket;
-        if (b >= (uint32_t)kNB) break;
+        if (s_bucket >= (uint32_t)kNB) break;
+        const uint32_t b = s_order[s_bucket];
         // Two 16-bit counters per word.  A counter is drained around 0x8000 (not at 0xFFFF) so that a carry can never
         // cross into its neighbour, whatever the interleaving of the other threads' updates (fewer than 32768 increments
         // can be in flight).  Eight items (one 128-bit load) at a time, branch-free: 8 shared atomics back to back, then 8 checks.
@@ -778,19 +816,23 @@ count_buckets_kernel(const uint16_t *__restrict__ gbuf, uint32_t cap_cb, const u
             if (lane == 0) seg = atomicAdd(&s_next_seg, 1u);
             seg = __shfl_sync(0xffffffffu, seg, 0);
             if (seg >= (uint32_t)n_seg) break;
-            const uint32_t n = min(gcount[(uint64_t)b * n_seg + seg], cap_cb);
-            const uint16_t *items = gbuf + ((uint64_t)b * n_seg + seg) * cap_cb;  // 16-byte aligned: cap_cb is a multiple of 8
-            const uint32_t n8 = n & ~7u;
-            for (uint32_t i = lane * 8u; i < n8; i += 1024u) {  // four 128-bit loads in flight per lane
-                uint4 v[4];
+            const uint2 fill = reinterpret_cast<const uint2 *>(gcount)[(uint64_t)b * n_seg + seg];
+            for (int part = 0; part < 2; ++part) {  // the flushed chunks at the front of the region, the direct appends behind cap_front
+                const uint32_t n = part ? min(fill.y, cap_cb - cap_front) : min(fill.x, cap_front);
+                if (!n) continue;
+                const uint16_t *items = gbuf + ((uint64_t)b * n_seg + seg) * cap_cb + (part ? cap_front : 0u);  // 16-byte aligned: both caps are multiples of 8
+                const uint32_t n8 = n & ~7u;
+                for (uint32_t i = lane * 8u; i < n8; i += 1024u) {  // four 128-bit loads in flight per lane
+                    uint4 v[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    v[u] = (i + 256u * u < n8) ? *reinterpret_cast<const uint4 *>(items + i + 256u * u) : make_uint4(0, 0, 0, 0);
+                    for (int u = 0; u < 4; ++u)
+                        v[u] = (i + 256u * u < n8) ? *reinterpret_cast<const uint4 *>(items + i + 256u * u) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (i + 256u * u < n8) add8(v[u]);
+                    for (int u = 0; u < 4; ++u)
+                        if (i + 256u * u < n8) add8(v[u]);
+                }
+                if ((uint32_t)lane < n - n8) add_item(items[n8 + lane]);
             }
-            if ((uint32_t)lane < n - n8) add_item(items[n8 + lane]);
         }
         __syncthreads();
         if constexpr (ItemFmt<S>::kCore) {
@@ -893,10 +935,10 @@ cudaError_t run_bucketed(const LaunchInfo &li, const BucketScratch &bs, const ui
     const uint64_t wspan = 32ull * 16 * S;
     const uint64_t n_witers = (hi - lo) / wspan;
     if (n_witers >> 32) return cudaErrorInvalidValue;  // the kernel counts a warp's iterations in 32 bits (a range of >= 2 TiB: not on this device)
-    cudaError_t e = cudaMemsetAsync(bs.work, 0, 16, st);
+    cudaError_t e = cudaMemsetAsync(bs.work, 0, 64 + kNB * sizeof(uint32_t), st);  // pass-2 work counter + per-bucket item totals
     if (e != cudaSuccess) return e;
-    bucketize_kernel<S><<<bs.n_cta * FKB_P1_MINBLOCKS, P1Cfg<S>::kThreads, sizeof(P1Smem), st>>>(d_stream, lo, n_witers, bs.gbuf, bs.cap_cb, bs.gcount, d_table, d_flags, d_partials);
-    count_buckets_kernel<S><<<li.sm_count, kP2Threads, 128 * 1024, st>>>(bs.gbuf, bs.cap_cb, bs.gcount, bs.n_cta * FKB_P1_MINBLOCKS, bs.table_w, d_table, bs.work);
+    bucketize_kernel<S><<<bs.n_cta * FKB_P1_MINBLOCKS, P1Cfg<S>::kThreads, sizeof(P1Smem), st>>>(d_stream, lo, n_witers, bs.gbuf, bs.cap_cb, bs.cap_front, bs.gcount, bs.work + 16, d_table, d_flags, d_partials);
+    count_buckets_kernel<S><<<li.sm_count, kP2Threads, 128 * 1024, st>>>(bs.gbuf, bs.cap_cb, bs.cap_front, bs.gcount, bs.n_cta * FKB_P1_MINBLOCKS, bs.table_w, d_table, bs.work);
     if (launches) *launches += 2;
     cudaError_t e2 = cudaGetLastError();
     if (e2 != cudaSuccess) return e2;

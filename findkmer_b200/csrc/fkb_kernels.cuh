@@ -16,10 +16,11 @@ enum CountVariant : int {
 // device scratch of VARIANT_BUCKET (owned by the context)
 struct BucketScratch {
     uint16_t *gbuf = nullptr;      // [n_buckets][n_cta][cap_cb] routed payloads: one private segment per (bucket, pass-1 CTA)
-    uint32_t cap_cb = 0;           // items per segment (multiple of 8)
+    uint32_t cap_cb = 0;           // items per segment (multiple of 8): [0, cap_front) flushed chunks, [cap_front, cap_cb) direct appends
+    uint32_t cap_front = 0;        // multiple of 8
     int n_cta = 0;                 // pass-1 grid size the layout was built for
-    uint32_t *gcount = nullptr;    // [n_buckets][n_cta] items in each segment
-    uint32_t *work = nullptr;      // pass-2 work counter
+    uint32_t *gcount = nullptr;    // [n_buckets][n_cta][2] items in the front / back part of each segment
+    uint32_t *work = nullptr;      // pass-2 work counter (word 0) and, from word 16 on, one item total per bucket
     uint16_t *table_w = nullptr;   // [4^W] 16-bit W-mer counts
     uint32_t *fold = nullptr;      // per-level (all, suf) arrays of the fold
 };

@@ -228,6 +228,19 @@ def test_bucketed_variant_skewed_input_exercises_every_escape(bucketed, harness,
     assert_counts_equal(got, want)
 
 
+@pytest.mark.parametrize("k", [8, 11])
+def test_bucketed_variant_skewed_composition_uses_the_back_region(bucketed, harness, k):
+    """A/T-rich i.i.d. sequence (0.35/0.15): the A/T-rich buckets are ~5x as popular as the average, their staging rows fill
+    up every tile and the surplus is appended straight to the back part of the bucket's region (and pass 2 takes the
+    buckets largest first); everything must stay exact"""
+    rng = np.random.default_rng(11)
+    s = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.choice(4, size=6_000_000, p=[0.35, 0.15, 0.15, 0.35])]
+    s = s.copy()
+    s[rng.integers(0, s.size, size=300)] = ord("N")
+    got, _ = _device_count(bucketed, s, k)
+    assert_counts_equal(got, harness.oracle_count_stream(s, k))
+
+
 def test_bucketed_and_direct_agree_on_config2(counter, harness):
     from findkmer_b200 import synth
     stream = counter.strip(synth.render(synth.config2()))
