@@ -109,7 +109,9 @@ int ensure_bucket_scratch(fkb_context *ctx, int k, uint64_t range_bytes)
     // (16.8 GB of the 180 GB for a 3.1 Gbp range at k = 11)
     uint64_t cap_front = (4 * (items / (nb * n_seg)) + 64 + 7) & ~7ull;
     if (cap_front > 0x3FFFFFF8ull) cap_front = 0x3FFFFFF8ull;
-    uint64_t cap = 2 * cap_front;
+    uint64_t back_percent = 100;  // FKB_BACK_PERCENT: size of the back part relative to the front part (tuning knob)
+    if (const char *e = getenv("FKB_BACK_PERCENT")) back_percent = (uint64_t)atoi(e);
+    uint64_t cap = cap_front + ((cap_front * back_percent / 100 + 7) & ~7ull);
     if (!fkb::bucket_folds_in_shared(k)) {  // k <= 8 only: the 16-bit 13-mer table (128 MiB) and the fold levels
         if (!ctx->bucket.table_w) FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.table_w, fkb::bucket_table_w_bytes()));
         if (!ctx->bucket.fold) FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.fold, fkb::bucket_fold_bytes()));

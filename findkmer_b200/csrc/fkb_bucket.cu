@@ -742,34 +742,45 @@ count_buckets_kernel(const uint16_t *__restrict__ gbuf, uint32_t cap_cb, uint32_
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t *sub = reinterpret_cast<uint32_t *>(smem_raw);  // 32768 words = 65536 packed 16-bit counters
     __shared__ uint32_t s_bucket, s_next_seg;
-    __shared__ uint32_t s_total[kNB];
-    __shared__ uint16_t s_order[kNB];
+    __shared__ uint32_t s_key[kNB];
+    __shared__ uint32_t s_max;
     const int lane = threadIdx.x & 31;
     const uint32_t sub_sa = (uint32_t)__cvta_generic_to_shared(sub);
-    // Largest bucket first (every CTA sorts the 1024 bucket sizes for itself: 55 compare-exchange steps, ~2 us): real genomes
-    // load the buckets unevenly (base composition, repeats), and a bucket several times the average that is started last
-    // would be the tail of the kernel.
+    // Largest buckets first: real genomes load the buckets unevenly (base composition, repeats), and a bucket several times the
+    // average that is started last would be the tail of the kernel.  Sizes are compared in 16 coarse classes (relative to the
+    // largest bucket) and ties keep the index order, so that on evenly loaded input the CTAs still sweep the bucket regions in
+    // address order (a random order costs ~3 % in pass 2: TLB / DRAM page locality).  Every CTA sorts the 1024 keys for itself
+    // (bitonic, 55 compare-exchange steps, of which 30 stay inside a warp).
     const uint32_t *bucket_total = work + 16;
-    for (int i = threadIdx.x; i < kNB; i += kP2Threads) { s_total[i] = bucket_total[i]; s_order[i] = (uint16_t)i; }
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < kNB; i += kP2Threads) atomicMax(&s_max, bucket_total[i]);
+    __syncthreads();
+    {
+        const uint32_t mx = s_max;
+        const int shift = mx >= 16 ? (32 - __clz(mx)) - 4 : 0;  // the largest bucket falls in class 8..15
+        for (int i = threadIdx.x; i < kNB; i += kP2Threads) s_key[i] = ((bucket_total[i] >> shift) << 10) | (uint32_t)(kNB - 1 - i);
+    }
     __syncthreads();
     for (int k2 = 2; k2 <= kNB; k2 <<= 1)
         for (int j = k2 >> 1; j > 0; j >>= 1) {
             for (int i = threadIdx.x; i < kNB; i += kP2Threads) {
                 const int ixj = i ^ j;
                 if (ixj > i) {
-                    const uint16_t a = s_order[i], c = s_order[ixj];
-                    const uint32_t ta = s_total[a], tc = s_total[c];
-                    if (((i & k2) == 0) ? (ta < tc) : (ta > tc)) { s_order[i] = c; s_order[ixj] = a; }
+                    const uint32_t a = s_key[i], c = s_key[ixj];
+                    if (((i & k2) == 0) ? (a < c) : (a > c)) { s_key[i] = c; s_key[ixj] = a; }  // descending overall
                 }
             }
-            __syncthreads();
+            // thread i owns element i (kP2Threads == kNB): exchanges at distance < 32 stay inside a warp's 32 elements
+            if (kP2Threads == kNB && j < 32 && (j >> 1) >= 1) __syncwarp();
+            else __syncthreads();
         }
     for (;;) {
         if (threadIdx.x == 0) { s_bucket = atomicAdd(work, 1u); s_next_seg = 0; }
         for (int i = threadIdx.x; i < 32768 / 4; i += kP2Threads) reinterpret_cast<uint4 *>(sub)[i] = make_uint4(0, 0, 0, 0);
         __syncthreads();
         if (s_bucket >= (uint32_t)kNB) break;
-        const uint32_t b = s_order[s_bucket];
+        const uint32_t b = (uint32_t)(kNB - 1) - (s_key[s_bucket] & (uint32_t)(kNB - 1));
         // Two 16-bit counters per word.  A counter is drained around 0x8000 (not at 0xFFFF) so that a carry can never
         // cross into its neighbour, whatever the interleaving of the other threads' updates (fewer than 32768 increments
         // can be in flight).  Eight items (one 128-bit load) at a time, branch-free: 8 shared atomics back to back, then 8 checks.
