@@ -311,7 +311,7 @@ struct P1Smem {
     uint32_t junk[32];     // directly behind cursor[]: one junk cursor per lane, the target of the slot atomic of an item that is NOT emitted
     uint32_t goff[kNB];    // items already appended to the FRONT part of this CTA's region of the bucket (multiple of 8 until the end)
     uint32_t gback[kNB];   // items written straight to the BACK part of the region because the staging row was full (skewed input)
-    uint32_t ev[16];       // per-run event counters (see group_events), flushed to the partials once per tile
+    uint32_t ev[16];       // per-run event counters (see warp_group_events), flushed to the partials once per tile
 };
 
 // shared-memory atomic / predicated store on 32-bit shared addresses: no branches, so the 8 atomics of a batch issue
