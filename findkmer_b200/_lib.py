@@ -26,7 +26,7 @@ FKB_ERR_ZERO_BASE_PROBABILITY = 9
 
 # every symbol include/findkmer_b200.h declares (tests check that the built library exports all of them)
 EXPORTS = [
-    "fkb_create", "fkb_destroy", "fkb_last_error", "fkb_status_string", "fkb_version", "fkb_device_info", "fkb_set_option",
+    "fkb_create", "fkb_destroy", "fkb_last_error", "fkb_status_string", "fkb_version", "fkb_device_info", "fkb_set_option", "fkb_phase_times",
     "fkb_strip_fasta", "fkb_alloc_pinned", "fkb_free_pinned",
     "fkb_table_entries", "fkb_prefix_flags_bytes", "fkb_zero_device", "fkb_count_stream_device", "fkb_finalize_device",
     "fkb_count_fasta_host", "fkb_count_stream_host", "fkb_count_fasta_host_range", "fkb_count_file",
@@ -95,6 +95,8 @@ def load() -> ctypes.CDLL:
     lib.fkb_device_info.restype = c_int
     lib.fkb_set_option.argtypes = [ctx, c_char_p, ctypes.c_long]
     lib.fkb_set_option.restype = c_int
+    lib.fkb_phase_times.argtypes = [ctx, POINTER(ctypes.c_double * 3)]
+    lib.fkb_phase_times.restype = c_int
     lib.fkb_strip_fasta.argtypes = [c_void_p, c_size_t, c_void_p, POINTER(c_size_t), c_int]
     lib.fkb_strip_fasta.restype = c_int
     lib.fkb_alloc_pinned.argtypes = [ctx, c_size_t, POINTER(c_void_p)]

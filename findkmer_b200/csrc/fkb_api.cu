@@ -526,6 +526,8 @@ void fkb_destroy(fkb_context *ctx)
     if (ctx->bucket.gbuf) cudaFree(ctx->bucket.gbuf);
     if (ctx->bucket.gcount) cudaFree(ctx->bucket.gcount);
     if (ctx->bucket.work) cudaFree(ctx->bucket.work);
+    for (int i = 0; i < 4; ++i)
+        if (ctx->bucket.phase_ev[i]) cudaEventDestroy(ctx->bucket.phase_ev[i]);
     if (ctx->bucket.table_w) cudaFree(ctx->bucket.table_w);
     if (ctx->bucket.fold) cudaFree(ctx->bucket.fold);
     if (ctx->d_stream) cudaFree(ctx->d_stream);
@@ -569,7 +571,31 @@ int fkb_set_option(fkb_context *ctx, const char *name, long value)
         ctx->loader_chunk = (size_t)value;
         return FKB_OK;
     }
+    if (!strcmp(name, "phase_events") && (value == 0 || value == 1)) {
+        FKB_CUDA(ctx, cudaSetDevice(ctx->device));
+        for (int i = 0; i < 4; ++i) {
+            if (value && !ctx->bucket.phase_ev[i]) FKB_CUDA(ctx, cudaEventCreate(&ctx->bucket.phase_ev[i]));
+            if (!value && ctx->bucket.phase_ev[i]) {
+                cudaEventDestroy(ctx->bucket.phase_ev[i]);
+                ctx->bucket.phase_ev[i] = nullptr;
+            }
+        }
+        return FKB_OK;
+    }
     return fail(ctx, FKB_ERR_BAD_ARG, "unknown option %s=%ld", name, value);
+}
+
+int fkb_phase_times(fkb_context *ctx, double ms[3])
+{
+    if (!ctx || !ms) return FKB_ERR_BAD_ARG;
+    if (!ctx->bucket.phase_ev[0]) return fail(ctx, FKB_ERR_BAD_ARG, "fkb_phase_times: option phase_events is off");
+    FKB_CUDA(ctx, cudaEventSynchronize(ctx->bucket.phase_ev[3]));
+    for (int i = 0; i < 3; ++i) {
+        float t = 0;
+        FKB_CUDA(ctx, cudaEventElapsedTime(&t, ctx->bucket.phase_ev[i], ctx->bucket.phase_ev[i + 1]));
+        ms[i] = t;
+    }
+    return FKB_OK;
 }
 
 int fkb_alloc_pinned(fkb_context *ctx, size_t bytes, void **ptr)

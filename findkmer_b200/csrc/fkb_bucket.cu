@@ -948,13 +948,19 @@ cudaError_t run_bucketed(const LaunchInfo &li, const BucketScratch &bs, const ui
     if (n_witers >> 32) return cudaErrorInvalidValue;  // the kernel counts a warp's iterations in 32 bits (a range of >= 2 TiB: not on this device)
     cudaError_t e = cudaMemsetAsync(bs.work, 0, 64 + kNB * sizeof(uint32_t), st);  // pass-2 work counter + per-bucket item totals
     if (e != cudaSuccess) return e;
+    const bool timed = bs.phase_ev[0] != nullptr;  // option "phase_events" (bench.py: live per-kernel durations)
+    if (timed) cudaEventRecord(bs.phase_ev[0], st);
     bucketize_kernel<S><<<bs.n_cta * FKB_P1_MINBLOCKS, P1Cfg<S>::kThreads, sizeof(P1Smem), st>>>(d_stream, lo, n_witers, bs.gbuf, bs.cap_cb, bs.cap_front, bs.gcount, bs.work + 16, d_table, d_flags, d_partials);
+    if (timed) cudaEventRecord(bs.phase_ev[1], st);
     count_buckets_kernel<S><<<li.sm_count, kP2Threads, 128 * 1024, st>>>(bs.gbuf, bs.cap_cb, bs.cap_front, bs.gcount, bs.n_cta * FKB_P1_MINBLOCKS, bs.table_w, d_table, bs.work);
     if (launches) *launches += 2;
     cudaError_t e2 = cudaGetLastError();
     if (e2 != cudaSuccess) return e2;
-    if constexpr (ItemFmt<S>::kCore) return cudaSuccess;  // pass 2 has already folded every bucket into T_k
-    else return run_fold<S>(li, bs, d_table, st, launches);
+    if (timed) cudaEventRecord(bs.phase_ev[2], st);
+    cudaError_t e3 = cudaSuccess;
+    if constexpr (!ItemFmt<S>::kCore) e3 = run_fold<S>(li, bs, d_table, st, launches);  // (core buckets: pass 2 has already folded into T_k)
+    if (timed) cudaEventRecord(bs.phase_ev[3], st);
+    return e3;
 }
 
 }  // namespace

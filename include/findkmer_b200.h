@@ -88,8 +88,13 @@ int fkb_device_info(fkb_context *ctx, int *sm_count, int *cc_major, int *cc_mino
  * The environment variable FKB_VARIANT sets the same knob at fkb_create time.
  * "loader": 0 = pinned host input is stripped on the GPU, pageable input by the host loader threads (default),
  * 1 = always the host loader, 2 = always the device loader (FKB_LOADER=host|device).
- * "loader_chunk": raw bytes per device-loader chunk (0 = 128 MiB). */
+ * "loader_chunk": raw bytes per device-loader chunk (0 = 128 MiB).
+ * "phase_events": 1 = record CUDA events around the kernels of the bucketed path (see fkb_phase_times). */
 int fkb_set_option(fkb_context *ctx, const char *name, long value);
+/* Profiling aid (no counterpart in the reference): with option "phase_events" = 1 the bucketed count path records CUDA events
+ * around its kernels; this returns the durations of the LAST such count call in milliseconds -- ms[0] pass 1 (bucketize),
+ * ms[1] pass 2 (count_buckets incl. the shared-memory fold), ms[2] fold kernels (k <= 8; 0 otherwise).  Synchronises. */
+int fkb_phase_times(fkb_context *ctx, double ms[3]);
 
 /* ---- host loader: the "stream contract" of findKmer()'s outer loop (:988-1011) ----------------
  * Drops every '\n'; turns each '>'...'\n' header into ONE '>' byte; stops at the first byte 0xFF

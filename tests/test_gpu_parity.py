@@ -241,6 +241,28 @@ def test_bucketed_variant_skewed_composition_uses_the_back_region(bucketed, harn
     assert_counts_equal(got, harness.oracle_count_stream(s, k))
 
 
+def test_phase_times_of_the_bucketed_path(bucketed):
+    """option phase_events: the library records CUDA events around pass 1 / pass 2 / fold; results unchanged"""
+    import ctypes
+    from findkmer_b200 import synth
+    stream = bucketed.strip(synth.render(synth.config2(n_bases=3_000_000)))
+    lib, ctx = bucketed._lib, bucketed._ctx
+    ms = (ctypes.c_double * 3)()
+    assert lib.fkb_phase_times(ctx, ctypes.byref(ms)) != 0  # off by default
+    want, _ = _device_count(bucketed, stream, 8)
+    assert lib.fkb_set_option(ctx, b"phase_events", 1) == 0
+    try:
+        got, _ = _device_count(bucketed, stream, 8)
+        assert lib.fkb_phase_times(ctx, ctypes.byref(ms)) == 0
+        assert ms[0] > 0 and ms[1] > 0 and ms[2] > 0  # k = 8: top-bit buckets, so the fold kernels run too
+        got11, _ = _device_count(bucketed, stream, 11)
+        assert lib.fkb_phase_times(ctx, ctypes.byref(ms)) == 0
+        assert ms[0] > 0 and ms[1] > 0 and ms[2] < 0.05  # core buckets: nothing between pass 2 and the end
+    finally:
+        assert lib.fkb_set_option(ctx, b"phase_events", 0) == 0
+    assert np.array_equal(got.table, want.table)
+
+
 def test_bucketed_and_direct_agree_on_config2(counter, harness):
     from findkmer_b200 import synth
     stream = counter.strip(synth.render(synth.config2()))
