@@ -57,6 +57,36 @@ __global__ void __launch_bounds__(kThreads, 1) k_flush_bulk(uint8_t *dst, int ro
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// half of the rows by the LSU, half by the bulk-copy engine, at the same time: do the two paths add up?
+__global__ void __launch_bounds__(kThreads, 1) k_flush_mixed(uint8_t *dst, int row_bytes, int tiles, int ring)
+{
+    extern __shared__ __align__(16) uint8_t sm[];
+    for (int i = threadIdx.x; i < kRows * kRowStride / 4; i += kThreads) reinterpret_cast<uint32_t *>(sm)[i] = i;
+    __syncthreads();
+    const uint32_t sm_sa = (uint32_t)__cvta_generic_to_shared(sm);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane >> 3, c = lane & 7;
+    const size_t seg = (size_t)ring * row_bytes;
+    for (int t = 0; t < tiles; ++t) {
+        if (warp < kThreads / 64) {  // rows [0, kRows/2): LSU copies
+            for (int b = warp * 4 + sub; b < kRows / 2; b += (kThreads / 64) * 4) {
+                uint8_t *d = dst + ((size_t)b * gridDim.x + blockIdx.x) * seg + (size_t)(t % ring) * row_bytes;
+                for (int i0 = c * 16; i0 < row_bytes; i0 += 128)
+                    *reinterpret_cast<uint4 *>(d + i0) = *reinterpret_cast<const uint4 *>(sm + b * kRowStride + i0);
+            }
+        } else {                     // rows [kRows/2, kRows): bulk copies
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            for (int b = kRows / 2 + (threadIdx.x - kThreads / 2); b < kRows; b += kThreads / 2) {
+                uint8_t *d = dst + ((size_t)b * gridDim.x + blockIdx.x) * seg + (size_t)(t % ring) * row_bytes;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(d), "r"(sm_sa + b * kRowStride), "r"(row_bytes) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        __syncthreads();
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 int main()
 {
     CK(cudaSetDevice(0));
@@ -66,6 +96,7 @@ int main()
     const int smem = kRows * kRowStride;
     CK(cudaFuncSetAttribute(k_flush_lsu, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CK(cudaFuncSetAttribute(k_flush_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(k_flush_mixed, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
@@ -78,11 +109,12 @@ int main()
         uint8_t *dst;
         CK(cudaMalloc(&dst, (size_t)kRows * sms * ring * 208));
         for (int row_bytes = 64; row_bytes <= 208; row_bytes += (row_bytes == 128 ? 80 : 64)) {
-            for (int mode = 0; mode < 2; ++mode) {
+            for (int mode = 0; mode < 3; ++mode) {
                 for (int rep = 0; rep < 2; ++rep) {
                     CK(cudaEventRecord(e0));
                     if (mode == 0) k_flush_lsu<<<grid, kThreads, smem>>>(dst, row_bytes, tiles, ring);
-                    else k_flush_bulk<<<grid, kThreads, smem>>>(dst, row_bytes, tiles, ring);
+                    else if (mode == 1) k_flush_bulk<<<grid, kThreads, smem>>>(dst, row_bytes, tiles, ring);
+                    else k_flush_mixed<<<grid, kThreads, smem>>>(dst, row_bytes, tiles, ring);
                     CK(cudaEventRecord(e1));
                     CK(cudaEventSynchronize(e1));
                     CK(cudaGetLastError());
@@ -91,7 +123,7 @@ int main()
                 CK(cudaEventElapsedTime(&ms, e0, e1));
                 const double us_tile = ms * 1e3 / tiles;
                 printf("{\"bench\": \"%s\", \"ctas\": %d, \"ring\": %d, \"row_bytes\": %d, \"us_per_tile\": %.3f, \"clk_per_row\": %.2f, \"chip_gbs\": %.0f}\n",
-                       mode ? "flush_bulk" : "flush_lsu", grid, ring, row_bytes, us_tile, us_tile * 1e-6 * prop.clockRate * 1e3 / kRows,
+                       mode == 0 ? "flush_lsu" : (mode == 1 ? "flush_bulk" : "flush_half_lsu_half_bulk"), grid, ring, row_bytes, us_tile, us_tile * 1e-6 * prop.clockRate * 1e3 / kRows,
                        (double)grid * kRows * row_bytes / us_tile * 1e-3);
             }
         }
