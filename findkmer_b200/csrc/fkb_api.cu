@@ -35,6 +35,8 @@ struct fkb_context {
 
     cudaStream_t s_pipe = nullptr;  // host pipeline: copies and kernels, in order
     cudaStream_t s_aux = nullptr;   // zeroing that may overlap the first copies
+    cudaStream_t s_edge = nullptr;  // the edge slivers of a bucketed range run here, next to pass 2
+    cudaEvent_t ev_edge_fork = nullptr, ev_edge_join = nullptr;
 
     // finalize scratch
     unsigned long long *d_scratch = nullptr;
@@ -92,7 +94,10 @@ int fail(fkb_context *ctx, int status, const char *fmt, ...)
             return fail((ctx), FKB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
 
-fkb::LaunchInfo launch_info(const fkb_context *ctx) { return fkb::LaunchInfo{ctx->sm_count, ctx->forced_variant, ctx->bucket}; }
+fkb::LaunchInfo launch_info(const fkb_context *ctx)
+{
+    return fkb::LaunchInfo{ctx->sm_count, ctx->forced_variant, ctx->bucket, ctx->s_edge, ctx->ev_edge_fork, ctx->ev_edge_join};
+}
 
 // Scratch of the bucketed path, sized for a range of `range_bytes` at word stride S: one private segment per
 // (bucket, pass-1 CTA) of 4x the average fill (real genomes are skewed; anything beyond escapes exactly through
@@ -495,6 +500,9 @@ int fkb_create(int device, fkb_context **out)
     ctx->loader_mode = l ? (!strcmp(l, "host") ? 1 : (!strcmp(l, "device") ? 2 : 0)) : 0;
     bool ok = cudaStreamCreateWithFlags(&ctx->s_pipe, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->s_edge, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_edge_fork, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_edge_join, cudaEventDisableTiming) == cudaSuccess &&
               cudaMalloc(&ctx->d_scratch, sizeof(unsigned long long) * fkb::kFinalizeScratchWords) == cudaSuccess &&
               cudaMalloc(&ctx->d_counts, sizeof(fkb_counts)) == cudaSuccess &&
               cudaHostAlloc((void **)&ctx->h_counts, sizeof(fkb_counts), cudaHostAllocDefault) == cudaSuccess;
@@ -539,6 +547,9 @@ void fkb_destroy(fkb_context *ctx)
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->s_pipe) cudaStreamDestroy(ctx->s_pipe);
     if (ctx->s_aux) cudaStreamDestroy(ctx->s_aux);
+    if (ctx->s_edge) cudaStreamDestroy(ctx->s_edge);
+    if (ctx->ev_edge_fork) cudaEventDestroy(ctx->ev_edge_fork);
+    if (ctx->ev_edge_join) cudaEventDestroy(ctx->ev_edge_join);
     delete ctx;
 }
 

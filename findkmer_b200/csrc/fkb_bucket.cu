@@ -775,12 +775,18 @@ count_buckets_kernel(const uint16_t *__restrict__ gbuf, uint32_t cap_cb, uint32_
             if (kP2Threads == kNB && j < 32 && (j >> 1) >= 1) __syncwarp();
             else __syncthreads();
         }
+    constexpr int kFillCache = 512;            // segments per bucket whose fills are staged in shared memory (148 on B200)
+    __shared__ uint2 s_fill[kFillCache];
     for (;;) {
         if (threadIdx.x == 0) { s_bucket = atomicAdd(work, 1u); s_next_seg = 0; }
-        for (int i = threadIdx.x; i < 32768 / 4; i += kP2Threads) reinterpret_cast<uint4 *>(sub)[i] = make_uint4(0, 0, 0, 0);
         __syncthreads();
         if (s_bucket >= (uint32_t)kNB) break;
         const uint32_t b = (uint32_t)(kNB - 1) - (s_key[s_bucket] & (uint32_t)(kNB - 1));
+        // zero the counters and stage the fills of the bucket's segments (one coalesced read instead of a dependent global
+        // load in front of every segment: with short segments -- small ranges, many GPUs -- that latency was most of a bucket)
+        for (int i = threadIdx.x; i < 32768 / 4; i += kP2Threads) reinterpret_cast<uint4 *>(sub)[i] = make_uint4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < n_seg && i < kFillCache; i += kP2Threads) s_fill[i] = reinterpret_cast<const uint2 *>(gcount)[(uint64_t)b * n_seg + i];
+        __syncthreads();
         // Two 16-bit counters per word.  A counter is drained around 0x8000 (not at 0xFFFF) so that a carry can never
         // cross into its neighbour, whatever the interleaving of the other threads' updates (fewer than 32768 increments
         // can be in flight).  Eight items (one 128-bit load) at a time, branch-free: 8 shared atomics back to back, then 8 checks.
@@ -827,7 +833,7 @@ count_buckets_kernel(const uint16_t *__restrict__ gbuf, uint32_t cap_cb, uint32_
             if (lane == 0) seg = atomicAdd(&s_next_seg, 1u);
             seg = __shfl_sync(0xffffffffu, seg, 0);
             if (seg >= (uint32_t)n_seg) break;
-            const uint2 fill = reinterpret_cast<const uint2 *>(gcount)[(uint64_t)b * n_seg + seg];
+            const uint2 fill = seg < (uint32_t)kFillCache ? s_fill[seg] : reinterpret_cast<const uint2 *>(gcount)[(uint64_t)b * n_seg + seg];
             for (int part = 0; part < 2; ++part) {  // the flushed chunks at the front of the region, the direct appends behind cap_front
                 const uint32_t n = part ? min(fill.y, cap_cb - cap_front) : min(fill.x, cap_front);
                 if (!n) continue;

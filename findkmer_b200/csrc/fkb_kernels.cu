@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(kThreads) count_direct_kernel(const uint8_t *_
     uint32_t *table = gtable;
     if constexpr (PRIV) {
         table = priv_table;
-        for (uint32_t i = threadIdx.x; i < (1u << (2 * k)); i += kThreads) priv_table[i] = 0;
+        for (uint32_t i = threadIdx.x; i < (1u << (2 * k)); i += blockDim.x) priv_table[i] = 0;
     }
     __syncthreads();
     const uint32_t mask = (k == 16) ? 0xffffffffu : ((1u << (2 * k)) - 1u);
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kThreads) count_direct_kernel(const uint8_t *_
     const uint64_t n_chunks = (end - base + kChunk - 1) / kChunk;
     Tally t = {0, 0, 0};
 
-    for (uint64_t c = (uint64_t)blockIdx.x * kThreads + threadIdx.x; c < n_chunks; c += (uint64_t)gridDim.x * kThreads) {
+    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += (uint64_t)gridDim.x * blockDim.x) {  // (any block size up to kThreads)
         const uint64_t p0 = base + c * kChunk;
         const bool edge = (p0 < begin) || (p0 + kChunk > end) || (p0 < 16);
         Scan sc = {0u, 0};
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kThreads) count_direct_kernel(const uint8_t *_
     }
     __syncthreads();
     if constexpr (PRIV) {
-        for (uint32_t i = threadIdx.x; i < (1u << (2 * k)); i += kThreads) {
+        for (uint32_t i = threadIdx.x; i < (1u << (2 * k)); i += blockDim.x) {
             const uint32_t v = priv_table[i];
             if (v) red_add_u32(gtable + i, v);
         }
@@ -418,11 +418,20 @@ inline int grid_for(uint64_t items_per_thread_units, int sm_count, int ctas_per_
 }  // namespace
 
 static cudaError_t launch_direct(const LaunchInfo &li, const uint8_t *d_stream, uint64_t begin, uint64_t end, uint64_t begin2, uint64_t end2,
-                                 int k, uint32_t *d_table, uint8_t *d_flags, fkb_partials *d_partials, cudaStream_t st, int *launches)
+                                 int k, uint32_t *d_table, uint8_t *d_flags, fkb_partials *d_partials, cudaStream_t st, int *launches,
+                                 bool slivers = false)
 {
     const uint64_t len1 = end > begin ? end - (begin & ~15ull) : 0, len2 = end2 > begin2 ? end2 - (begin2 & ~15ull) : 0;
     const uint64_t longest = len1 > len2 ? len1 : len2;
     if (!longest) return cudaSuccess;
+    if (slivers) {
+        // the two edge slivers of a bucketed interior (< 2 KiB each): 64-thread blocks, so that they fit on an SM next to a pass-2
+        // CTA (1024 threads x 56 registers) and run on the side stream while pass 2 counts
+        dim3 grid((unsigned)((longest + kChunk * 64 - 1) / (kChunk * 64)), len2 ? 2 : 1);
+        count_direct_kernel<false><<<grid, 64, 0, st>>>(d_stream, begin, end, begin2, end2, k, d_table, d_flags, d_partials);
+        if (launches) ++*launches;
+        return cudaGetLastError();
+    }
     if (k <= 7 && longest >= (256u << 10)) {  // private counters pay from a few hundred KiB on (every CTA adds its 4^k bins at the end)
         if (k == 7) {  // 64 KiB of dynamic shared memory needs the opt-in (per device, so not cached in a static)
             cudaError_t e = cudaFuncSetAttribute(count_direct_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
@@ -467,8 +476,23 @@ cudaError_t launch_count(const LaunchInfo &li, const uint8_t *d_stream, uint64_t
         bucket = hi > lo && hi - lo >= min_bytes;
     }
     if (!bucket) return launch_direct(li, d_stream, begin, end, 0, 0, k, d_table, d_flags, d_partials, st, launches);
-    // the two edge slivers go through the direct kernel (it owns every ragged / unaligned / short-halo case), in one launch
-    cudaError_t e = launch_direct(li, d_stream, begin, lo, hi, end, k, d_table, d_flags, d_partials, st, launches);
+    // The two edge slivers go through the direct kernel (it owns every ragged / unaligned / short-halo case), in one launch --
+    // on a side stream forked here and joined at the end, so that its ~25 us of latency-bound work hides behind pass 2
+    // instead of standing in front of pass 1 (2 % of a 3.1 Gbp step, 10 % of a 1/8 shard).
+    if (li.edge_stream) {
+        cudaError_t e = cudaEventRecord(li.edge_fork, st);  // the slivers depend on what precedes this call (zeroing), not on the big kernels
+        if (e != cudaSuccess) return e;
+        e = launch_count_bucketed(li, li.bucket, d_stream, lo, hi, k, d_table, d_flags, d_partials, st, launches);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamWaitEvent(li.edge_stream, li.edge_fork, 0);
+        if (e != cudaSuccess) return e;
+        e = launch_direct(li, d_stream, begin, lo, hi, end, k, d_table, d_flags, d_partials, li.edge_stream, launches, true);
+        if (e != cudaSuccess) return e;
+        e = cudaEventRecord(li.edge_join, li.edge_stream);
+        if (e != cudaSuccess) return e;
+        return cudaStreamWaitEvent(st, li.edge_join, 0);
+    }
+    cudaError_t e = launch_direct(li, d_stream, begin, lo, hi, end, k, d_table, d_flags, d_partials, st, launches, true);
     if (e != cudaSuccess) return e;
     return launch_count_bucketed(li, li.bucket, d_stream, lo, hi, k, d_table, d_flags, d_partials, st, launches);
 }

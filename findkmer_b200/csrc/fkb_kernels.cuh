@@ -30,6 +30,8 @@ struct LaunchInfo {
     int sm_count;
     int variant;          // forced variant (VARIANT_AUTO = choose)
     BucketScratch bucket; // valid when bucket.gbuf != nullptr
+    cudaStream_t edge_stream = nullptr;                      // side stream for the edge slivers of a bucketed range (nullptr: same stream)
+    cudaEvent_t edge_fork = nullptr, edge_join = nullptr;
 };
 
 int bucket_stride_for(int k);        // S = W - k + 1 when the bucketed path supports k, else 0
