@@ -5,7 +5,7 @@
         --log-file gpurun_out/traffic.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline
     python profiles/tools/traffic_summary.py gpurun_out/traffic.csv > profiles/rNN_traffic_k11.json
 
-Takes the kernels of the LAST step (from the last count_direct_kernel launch, which starts a step, to the end of the capture) and prints the JSON bench.py reads for `roofline.traffic`."""
+Takes the kernels of the LAST step (from the last bucketize_kernel launch, which starts a step, to the end of the capture) and prints the JSON bench.py reads for `roofline.traffic`."""
 import csv
 import json
 import re
@@ -21,10 +21,11 @@ def main():
         d["unit_" + r[12]] = r[13]
     ids = sorted(launches)
     names = [launches[i]["kernel"] for i in ids]
-    # a step = [count_direct_kernel (the edge slivers), bucketize, count_buckets, (fold levels), finalize levels]: take the last one
-    starts = [i for i, n in zip(ids, names) if "count_direct_kernel" in n]
+    # a step = [bucketize, count_buckets, count_direct_kernel (the edge slivers, side stream), (fold levels), finalize levels]: take the last one
+    # (the edge slivers' count_direct_kernel runs on a side stream and may be listed after the bucketed kernels)
+    starts = [i for i, n in zip(ids, names) if "bucketize_kernel" in n] or [i for i, n in zip(ids, names) if "count_direct_kernel" in n]
     if not starts:
-        sys.exit("no count_direct_kernel launch in the capture")
+        sys.exit("no count kernel launch in the capture")
     step = [i for i in ids if i >= starts[-1] and ("fkb" in launches[i]["kernel"] or "unnamed" in launches[i]["kernel"])]
     kernels, total = [], 0
     for i in step:
