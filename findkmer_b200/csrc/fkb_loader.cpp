@@ -134,23 +134,120 @@ __attribute__((target("avx2"))) StripResult strip_avx2(const uint8_t *buf, size_
     return {o, SIZE_MAX, in_header};
 }
 
-bool have_avx2()
+// AVX-512 VBMI2 scan: 64 bytes per step, line breaks squeezed out in registers (vpcompressb), so a step costs the
+// same whether the 64 bytes hold zero, one or two '\n'; only '>' and 0xFF leave the vector loop.
+template <bool WRITE>
+__attribute__((target("avx512f,avx512bw,avx512vbmi2,popcnt,bmi")))
+StripResult strip_avx512(const uint8_t *buf, size_t a, size_t b, bool in_header, uint8_t *out)
 {
-    static const bool v = __builtin_cpu_supports("avx2");
-    return v;
+    __m512i v_nl = _mm512_set1_epi8('\n'), v_gt = _mm512_set1_epi8('>'), v_ff = _mm512_set1_epi8((char)0xFF);
+    asm("" : "+v"(v_nl), "+v"(v_gt), "+v"(v_ff));  // keep the three constants in registers (gcc -O2 re-broadcasts them per step)
+    size_t o = 0, p = a;
+    while (p < b) {
+        if (in_header) {
+            const uint8_t *nl = (const uint8_t *)memchr(buf + p, '\n', b - p);
+            if (!nl) return {o, SIZE_MAX, true};
+            p = (size_t)(nl - buf) + 1;
+            in_header = false;
+            continue;
+        }
+        // two vectors per step while nothing but line breaks shows up (the body of a record)
+        while (p + 128 <= b) {
+            __m512i v0 = _mm512_loadu_si512((const void *)(buf + p)), v1 = _mm512_loadu_si512((const void *)(buf + p + 64));
+            // '>' = 0x3E and 0xFF both have bits 0x3E set: one compare finds a superset (also '?', '~', DEL, some high bytes)
+            __m512i miss = _mm512_min_epu8(_mm512_andnot_si512(v0, v_gt), _mm512_andnot_si512(v1, v_gt));  // 0 where all six bits are set
+            if (_mm512_testn_epi8_mask(miss, miss)) break;
+            uint64_t k0 = _mm512_cmpneq_epi8_mask(v0, v_nl), k1 = _mm512_cmpneq_epi8_mask(v1, v_nl);
+            size_t n0 = (size_t)__builtin_popcountll(k0);
+            if (WRITE) {
+                _mm512_storeu_si512((void *)(out + o), _mm512_maskz_compress_epi8((__mmask64)k0, v0));
+                _mm512_storeu_si512((void *)(out + o + n0), _mm512_maskz_compress_epi8((__mmask64)k1, v1));
+            }
+            o += n0 + (size_t)__builtin_popcountll(k1);
+            p += 128;
+        }
+        if (p + 64 <= b) {
+            __m512i v = _mm512_loadu_si512((const void *)(buf + p));
+            uint64_t keep = ~_mm512_cmpeq_epi8_mask(v, v_nl);
+            uint64_t stop = _mm512_cmpeq_epi8_mask(v, v_gt) | _mm512_cmpeq_epi8_mask(v, v_ff);
+            if (__builtin_expect(stop == 0, 1)) {
+                // whole-vector store: o + 64 <= (p - a) + 64 <= b - a, and the bytes past the kept ones are
+                // overwritten by the next step of this same block
+                if (WRITE) _mm512_storeu_si512((void *)(out + o), _mm512_maskz_compress_epi8((__mmask64)keep, v));
+                o += (size_t)__builtin_popcountll(keep);
+                p += 64;
+                continue;
+            }
+            unsigned t = (unsigned)__builtin_ctzll(stop);
+            keep &= (1ull << t) - 1;
+            if (WRITE) _mm512_storeu_si512((void *)(out + o), _mm512_maskz_compress_epi8((__mmask64)keep, v));
+            o += (size_t)__builtin_popcountll(keep);
+            uint8_t c = buf[p + t];
+            size_t q = p + t;
+            p = q + 1;
+            if (c == '>') {
+                if (WRITE) out[o] = '>';
+                ++o;
+                in_header = true;
+            } else {
+                return {o, q, false};
+            }
+            continue;
+        }
+        // tail shorter than one vector
+        size_t q = next_special_scalar(buf, p, b);
+        if (WRITE) memcpy(out + o, buf + p, q - p);
+        o += q - p;
+        if (q == b) break;
+        uint8_t c = buf[q];
+        p = q + 1;
+        if (c == '>') {
+            if (WRITE) out[o] = '>';
+            ++o;
+            in_header = true;
+        } else if (c == 0xFF) {
+            return {o, q, false};
+        }
+    }
+    return {o, SIZE_MAX, in_header};
+}
+
+// 0 = scalar, 1 = AVX2, 2 = AVX-512 VBMI2.  FKB_STRIP_ISA=scalar|avx2|avx512 lowers it; it is read per block (4 MiB of
+// work), so the tests can walk all three paths inside one process.
+int strip_isa()
+{
+    static const int best = [] {
+        int v = 0;
+        if (__builtin_cpu_supports("avx2")) v = 1;
+        if (v == 1 && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vbmi2")) v = 2;
+        return v;
+    }();
+    if (const char *env = getenv("FKB_STRIP_ISA")) {
+        int want = !strcmp(env, "scalar") ? 0 : !strcmp(env, "avx2") ? 1 : best;
+        return want < best ? want : best;
+    }
+    return best;
 }
 
 }  // namespace
 
-// `out` must have room for (b - a) + 32 bytes: the vector path stores whole 32-byte words.
+// `out` must have room for (b - a) + 32 bytes: the vector paths store whole 32- or 64-byte words.
 StripResult strip_block(const uint8_t *buf, size_t a, size_t b, bool in_header, uint8_t *out)
 {
-    return have_avx2() ? strip_avx2<true>(buf, a, b, in_header, out) : strip_scalar<true>(buf, a, b, in_header, out);
+    switch (strip_isa()) {
+    case 2: return strip_avx512<true>(buf, a, b, in_header, out);
+    case 1: return strip_avx2<true>(buf, a, b, in_header, out);
+    default: return strip_scalar<true>(buf, a, b, in_header, out);
+    }
 }
 
 StripResult strip_block_count(const uint8_t *buf, size_t a, size_t b, bool in_header)
 {
-    return have_avx2() ? strip_avx2<false>(buf, a, b, in_header, nullptr) : strip_scalar<false>(buf, a, b, in_header, nullptr);
+    switch (strip_isa()) {
+    case 2: return strip_avx512<false>(buf, a, b, in_header, nullptr);
+    case 1: return strip_avx2<false>(buf, a, b, in_header, nullptr);
+    default: return strip_scalar<false>(buf, a, b, in_header, nullptr);
+    }
 }
 
 }  // namespace fkb

@@ -49,7 +49,40 @@ def test_product_does_not_touch_the_oracle():
 
 
 # ---- the host loader: stream contract ------------------------------------------------------------------
-def test_strip_matches_contract_on_golden_inputs(harness, golden, test_txt):
+@pytest.fixture(params=["scalar", "avx2", "native"])
+def strip_isa(request, monkeypatch):
+    """the loader picks its widest vector path at run time (fkb_loader.cpp); FKB_STRIP_ISA lowers it per call"""
+    if request.param != "native":
+        monkeypatch.setenv("FKB_STRIP_ISA", request.param)
+    else:
+        monkeypatch.delenv("FKB_STRIP_ISA", raising=False)
+    return request.param
+
+
+def test_strip_dense_special_bytes(harness, strip_isa):
+    """vector steps with many line breaks, '>' and 0xFF per word, and the bytes the 0x3E-bit prefilter also catches"""
+    from findkmer_b200.engine import KmerCounter
+    rng = np.random.default_rng(7)
+    compared = 0
+    alphabet = np.frombuffer(b"ACGTNacgt\n\n\n>?~\x7f\xbe\xbf\xfe\x3f", dtype=np.uint8)
+    for n in (1, 63, 64, 65, 127, 128, 129, 191, 192, 193, 1000, 70_000):
+        for trial in range(6):
+            data = alphabet[rng.integers(0, len(alphabet), n)].copy()
+            if trial in (2, 3, 5):  # sparse: long clean runs between the special bytes (the two-vector inner loop)
+                data[rng.random(n) < 0.985] = ord("G")
+            if trial % 2:
+                data[rng.integers(0, n)] = 0xFF
+            if trial >= 4:
+                data[data == ord(">")] = ord("A")  # no headers: the 0xFF ends the scan wherever it is
+            data[-1] = ord("\n")
+            rc, want = harness.oracle_strip(data)
+            if rc == harness.FKO_OK:
+                assert bytes(KmerCounter.strip(data, 2)) == bytes(want), (n, trial)
+                compared += 1
+    assert compared >= 60
+
+
+def test_strip_matches_contract_on_golden_inputs(harness, golden, test_txt, strip_isa):
     from findkmer_b200 import FindKmerError, _lib
     from findkmer_b200.engine import KmerCounter
     inputs = [test_txt] + [r["input_latin1"].encode("latin1") for r in golden["micro"]] + [random_fasta(s, 9000) for s in range(4)]
@@ -65,7 +98,7 @@ def test_strip_matches_contract_on_golden_inputs(harness, golden, test_txt):
 
 
 @pytest.mark.parametrize("threads", [1, 3, 8])
-def test_strip_block_boundaries(harness, threads):
+def test_strip_block_boundaries(harness, threads, strip_isa):
     """> 4 MiB inputs cross loader blocks: headers, newlines and 0xFF placed on and around the block edges"""
     from findkmer_b200 import synth
     from findkmer_b200.engine import KmerCounter
@@ -86,7 +119,7 @@ def test_strip_block_boundaries(harness, threads):
     assert np.array_equal(got, want) and len(got) < 9_000_000
 
 
-def test_strip_giant_lines_and_header_only(harness):
+def test_strip_giant_lines_and_header_only(harness, strip_isa):
     from findkmer_b200.engine import KmerCounter
     one_line = b">h\n" + b"ACGT" * 3_000_000 + b"\n"
     assert np.array_equal(KmerCounter.strip(one_line, 4), harness.oracle_strip(one_line)[1])
