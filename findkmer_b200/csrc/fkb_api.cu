@@ -63,10 +63,11 @@ struct fkb_context {
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_strip[2] = {nullptr, nullptr};
 
     // pinned staging ring for the loader
-    static constexpr int kSlots = 12;
+    static constexpr int kMaxSlots = 64;
+    int n_slots = 24;  // ring size in use (option "loader_slots"); slots are allocated on first need
     size_t slot_bytes = 0;
-    uint8_t *slots[kSlots] = {nullptr};
-    cudaEvent_t slot_free[kSlots] = {nullptr};
+    uint8_t *slots[kMaxSlots] = {nullptr};
+    cudaEvent_t slot_free[kMaxSlots] = {nullptr};
 };
 
 namespace {
@@ -171,11 +172,12 @@ int ensure_stream(fkb_context *ctx, size_t bytes)
     return FKB_OK;
 }
 
-int ensure_slots(fkb_context *ctx)
+// the first `want` slots of the ring (a small file pins only what it uses)
+int ensure_slots(fkb_context *ctx, int want)
 {
-    if (ctx->slots[0]) return FKB_OK;
     ctx->slot_bytes = kBlockBytes + 64;
-    for (int i = 0; i < fkb_context::kSlots; ++i) {
+    for (int i = 0; i < want; ++i) {
+        if (ctx->slots[i]) continue;
         FKB_CUDA(ctx, cudaHostAlloc((void **)&ctx->slots[i], ctx->slot_bytes, cudaHostAllocDefault));
         FKB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->slot_free[i], cudaEventDisableTiming));
     }
@@ -325,17 +327,18 @@ static int pipeline_range(fkb_context *ctx, const uint8_t *fasta, size_t len, si
     *stop_offset = UINT64_MAX;
     *ends_in_header_out = 0;
     if (int s = ensure_stream(ctx, (len - own_offset) + 16 + 64)) return s;
-    if (int s = ensure_slots(ctx)) return s;
+    const size_t span = len - own_offset;
+    const size_t n_blocks = (span + kBlockBytes - 1) / kBlockBytes;
+    const int n_slots = (size_t)ctx->n_slots < n_blocks ? ctx->n_slots : (int)n_blocks;
+    if (int s = ensure_slots(ctx, n_slots)) return s;
 
     uint8_t halo[16];
     if (!left_halo(fasta, own_offset, halo, stop_offset)) return FKB_OK;  // the scan ended before this shard begins: it owns nothing
     FKB_CUDA(ctx, cudaMemcpyAsync(ctx->d_stream, halo, 16, cudaMemcpyHostToDevice, ctx->s_pipe));
     FKB_CUDA(ctx, cudaStreamSynchronize(ctx->s_pipe));  // halo[] is a stack buffer
 
-    const size_t span = len - own_offset;
-    const size_t n_blocks = (span + kBlockBytes - 1) / kBlockBytes;
-    const int n_slots = fkb_context::kSlots;
     int n_threads = fkb::default_host_threads();
+    if (n_threads >= 8 && !getenv("FKB_HOST_THREADS")) --n_threads;  // one core stays with the committing thread
     if ((size_t)n_threads > n_blocks) n_threads = (int)n_blocks;
 
     struct Task { fkb::StripResult r; bool done = false; };
@@ -498,6 +501,8 @@ int fkb_create(int device, fkb_context **out)
     ctx->forced_variant = v ? atoi(v) : 0;
     const char *l = getenv("FKB_LOADER");
     ctx->loader_mode = l ? (!strcmp(l, "host") ? 1 : (!strcmp(l, "device") ? 2 : 0)) : 0;
+    if (const char *ns = getenv("FKB_LOADER_SLOTS"))
+        if (atoi(ns) >= 2 && atoi(ns) <= fkb_context::kMaxSlots) ctx->n_slots = atoi(ns);
     bool ok = cudaStreamCreateWithFlags(&ctx->s_pipe, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->s_edge, cudaStreamNonBlocking) == cudaSuccess &&
@@ -519,7 +524,7 @@ void fkb_destroy(fkb_context *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < fkb_context::kSlots; ++i) {
+    for (int i = 0; i < fkb_context::kMaxSlots; ++i) {
         if (ctx->slots[i]) cudaFreeHost(ctx->slots[i]);
         if (ctx->slot_free[i]) cudaEventDestroy(ctx->slot_free[i]);
     }
@@ -580,6 +585,10 @@ int fkb_set_option(fkb_context *ctx, const char *name, long value)
     }
     if (!strcmp(name, "loader_chunk") && value >= 0 && (size_t)value <= kRawChunkBytes) {
         ctx->loader_chunk = (size_t)value;
+        return FKB_OK;
+    }
+    if (!strcmp(name, "loader_slots") && value >= 2 && value <= fkb_context::kMaxSlots) {
+        ctx->n_slots = (int)value;
         return FKB_OK;
     }
     if (!strcmp(name, "phase_events") && (value == 0 || value == 1)) {

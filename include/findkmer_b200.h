@@ -89,6 +89,7 @@ int fkb_device_info(fkb_context *ctx, int *sm_count, int *cc_major, int *cc_mino
  * "loader": 0 = pinned host input is stripped on the GPU, pageable input by the host loader threads (default),
  * 1 = always the host loader, 2 = always the device loader (FKB_LOADER=host|device).
  * "loader_chunk": raw bytes per device-loader chunk (0 = 128 MiB).
+ * "loader_slots": 4 MiB pinned slots of the host loader's ring, 2..64 (default 24; FKB_LOADER_SLOTS).
  * "phase_events": 1 = record CUDA events around the kernels of the bucketed path (see fkb_phase_times). */
 int fkb_set_option(fkb_context *ctx, const char *name, long value);
 /* Profiling aid (no counterpart in the reference): with option "phase_events" = 1 the bucketed count path records CUDA events
