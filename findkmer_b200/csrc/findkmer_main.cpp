@@ -19,6 +19,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -190,8 +191,20 @@ void print_memory_estimate(const Config &cfg)  // estimate_RAM_usage, :1256-1289
 
 }  // namespace
 
+// FKB_TIMING=1: wall-clock phases of the program on stderr (profiling aid; nothing is printed otherwise)
+static void phase_mark(const char *what)
+{
+    static const bool on = getenv("FKB_TIMING") != nullptr;
+    static auto last = std::chrono::steady_clock::now();
+    if (!on) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[timing] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
+    last = now;
+}
+
 int main(int argc, char **argv)
 {
+    phase_mark("start");
     Config cfg;
     usage();  // the reference prints usage on every run (:1301)
     if (!parse_arguments(argc, argv, cfg)) {
@@ -252,6 +265,7 @@ int main(int argc, char **argv)
         fclose(csv);
         return EXIT_FAILURE;
     }
+    phase_mark("fkb_create (CUDA context)");
     std::vector<int> ks = cfg.sweep.empty() ? std::vector<int>{cfg.k} : cfg.sweep;
     std::vector<std::vector<uint32_t>> tables(ks.size());
     std::vector<uint32_t *> table_ptrs(ks.size());
@@ -268,6 +282,7 @@ int main(int argc, char **argv)
     memset(all_counts.data(), 0, sizeof(fkb_counts) * ks.size());
     if (ks.size() == 1) status = fkb_count_file(ctx, cfg.sequence_file.c_str(), ks[0], table_ptrs[0], &all_counts[0]);
     else status = fkb_count_file_multi(ctx, cfg.sequence_file.c_str(), ks.data(), (int)ks.size(), table_ptrs.data(), all_counts.data());
+    phase_mark("count (mmap, load, GPU)");
     if (status == FKB_ERR_EMPTY_INPUT) {
         fprintf(stderr, "Sequence File Is Empty, Ending Program");  // :983
         fclose(csv);
@@ -289,6 +304,7 @@ int main(int argc, char **argv)
         return EXIT_FAILURE;
     }
     fkb_destroy(ctx);
+    phase_mark("fkb_destroy");
     if (all_counts[0].unknown_chars)
         fprintf(stderr, "Unknown character processed! File may be corrupted. (%llu such characters; the reference prints one line each)\n",
                 (unsigned long long)all_counts[0].unknown_chars);
@@ -348,6 +364,7 @@ int main(int argc, char **argv)
         csv = nullptr;
         fprintf(stdout, "Your file can be found in the current directory as: \n    %s\n", out_name.c_str());
     }
+    phase_mark("statistics + histogram files");
     if (exit_code == 0) fprintf(stdout, "End of program was reached properly.\n\n");
     fprintf(stderr, " ");
     return exit_code;
