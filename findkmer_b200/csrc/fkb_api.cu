@@ -14,6 +14,7 @@
 #include <unistd.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <string>
@@ -65,7 +66,6 @@ struct fkb_context {
     // pinned staging ring for the loader
     static constexpr int kMaxSlots = 64;
     int n_slots = 24;  // ring size in use (option "loader_slots"); slots are allocated on first need
-    size_t slot_bytes = 0;
     uint8_t *slots[kMaxSlots] = {nullptr};
     cudaEvent_t slot_free[kMaxSlots] = {nullptr};
 };
@@ -103,6 +103,17 @@ fkb::LaunchInfo launch_info(const fkb_context *ctx)
 // Scratch of the bucketed path, sized for a range of `range_bytes` at word stride S: one private segment per
 // (bucket, pass-1 CTA) of 4x the average fill (real genomes are skewed; anything beyond escapes exactly through
 // global reds), the segment fills and the 16-bit W-mer table.  HBM is plentiful: 3.1 Gbp at k = 11 takes ~8.4 GB.
+// FKB_TIMING=1: wall-clock marks of the host path on stderr (profiling aid, see profiles/tools/cli_probe.py)
+void phase_mark(const char *what)
+{
+    static const bool on = getenv("FKB_TIMING") != nullptr;
+    static auto last = std::chrono::steady_clock::now();
+    if (!on) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[timing]   lib: %-21s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
+    last = now;
+}
+
 int ensure_bucket_scratch(fkb_context *ctx, int k, uint64_t range_bytes)
 {
     const int S = fkb::bucket_stride_for(k);
@@ -172,13 +183,13 @@ int ensure_stream(fkb_context *ctx, size_t bytes)
     return FKB_OK;
 }
 
-// the first `want` slots of the ring (a small file pins only what it uses)
+// the first `want` slots of the ring (a small file pins only what it uses).  Allocating them lazily from the worker
+// threads was tried and is slower: cudaHostAlloc calls next to the running copies stall both.
 int ensure_slots(fkb_context *ctx, int want)
 {
-    ctx->slot_bytes = kBlockBytes + 64;
     for (int i = 0; i < want; ++i) {
         if (ctx->slots[i]) continue;
-        FKB_CUDA(ctx, cudaHostAlloc((void **)&ctx->slots[i], ctx->slot_bytes, cudaHostAllocDefault));
+        FKB_CUDA(ctx, cudaHostAlloc((void **)&ctx->slots[i], kBlockBytes + 64, cudaHostAllocDefault));
         FKB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->slot_free[i], cudaEventDisableTiming));
     }
     return FKB_OK;
@@ -203,6 +214,7 @@ int finish_host(fkb_context *ctx, int k, uint64_t stream_bytes, uint32_t *table,
     FKB_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, sizeof(fkb_counts), cudaMemcpyDeviceToHost, ctx->s_pipe));
     FKB_CUDA(ctx, cudaStreamSynchronize(ctx->s_pipe));
     *counts = *ctx->h_counts;
+    phase_mark("finalize + D2H + sync");
     return status_from_counts(ctx, *counts);
 }
 
@@ -326,11 +338,14 @@ static int pipeline_range(fkb_context *ctx, const uint8_t *fasta, size_t len, si
     *stream_bytes = 0;
     *stop_offset = UINT64_MAX;
     *ends_in_header_out = 0;
+    phase_mark("(enter pipeline)");
     if (int s = ensure_stream(ctx, (len - own_offset) + 16 + 64)) return s;
+    phase_mark("device stream alloc");
     const size_t span = len - own_offset;
     const size_t n_blocks = (span + kBlockBytes - 1) / kBlockBytes;
     const int n_slots = (size_t)ctx->n_slots < n_blocks ? ctx->n_slots : (int)n_blocks;
     if (int s = ensure_slots(ctx, n_slots)) return s;
+    phase_mark("pinned slots");
 
     uint8_t halo[16];
     if (!left_halo(fasta, own_offset, halo, stop_offset)) return FKB_OK;  // the scan ended before this shard begins: it owns nothing
@@ -441,6 +456,7 @@ static int pipeline_range(fkb_context *ctx, const uint8_t *fasta, size_t len, si
     }
     *stream_bytes = dev_off - 16;
     *ends_in_header_out = ends_in_header ? 1 : 0;
+    phase_mark("strip + H2D + count issue");
     return FKB_OK;
 }
 
@@ -815,6 +831,14 @@ int fkb_count_fasta_host_multi(fkb_context *ctx, const uint8_t *fasta, size_t le
     if (ends_in_header) {
         cudaStreamSynchronize(ctx->s_pipe);
         return fail(ctx, FKB_ERR_UNTERMINATED_HEADER, "%s", fkb_status_string(FKB_ERR_UNTERMINATED_HEADER));
+    }
+    // size the bucket regions once, for the k that needs the most (the largest k: smallest stride, most items),
+    // instead of growing them -- cudaFree + cudaMalloc of up to 12.6 GB -- at every step of an ascending sweep
+    {
+        int k_max = 0;
+        for (int i = 0; i < n_k; ++i) k_max = ks[i] > k_max && fkb::bucket_stride_for(ks[i]) ? ks[i] : k_max;
+        if (k_max)
+            if (int s = ensure_bucket_scratch(ctx, k_max, stream_bytes)) return s;
     }
     int worst = FKB_OK;
     for (int i = 0; i < n_k; ++i) {

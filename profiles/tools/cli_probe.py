@@ -23,14 +23,15 @@ c.synth_fasta_device(synth.config4(n_bases=n_bases)).cpu().numpy().tofile(fa)
 del c
 print(f"file {fa.stat().st_size/1e9:.3f} GB, {n_bases/1e9:.2f} Gbases, host cores {os.cpu_count()}")
 exe = ROOT / "findkmer_b200" / "bin" / "findKmer"
-for args in (["-k", "11"], ["-k", "11"], ["-k", "6"], ["-K", "6-11"]):
+runs = [(["-k", "11"], {}), (["-k", "11"], {}), (["-k", "11"], {"FKB_LOADER_SLOTS": "12"}), (["-k", "6"], {}), (["-K", "6-11"], {})]
+for args, extra_env in runs:
     t0 = time.perf_counter()
     r = subprocess.run([str(exe), "-q", "1", *args, "-z", "1000", "-p", fa.name], cwd=work, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
-                       env=dict(os.environ, FKB_TIMING="1"), text=True)
+                       env=dict(os.environ, FKB_TIMING="1", **extra_env), text=True)
     dt = time.perf_counter() - t0
     print("".join(l + "\n" for l in r.stdout.splitlines() if l.startswith("[timing]")), end="")
     outs = sorted(p.name + f" ({p.stat().st_size/1e6:.1f} MB)" for p in work.iterdir() if p.name != fa.name)
-    print(f"findKmer -q 1 {' '.join(args)} -z 1000 -p {fa.name}: rc={r.returncode} {dt:6.2f} s wall; files: {len(outs)}")
+    print(f"{' '.join(k + '=' + v for k, v in extra_env.items())} findKmer -q 1 {' '.join(args)} -z 1000 -p {fa.name}: rc={r.returncode} {dt:6.2f} s wall; files: {len(outs)}")
     for p in work.iterdir():
         if p.name != fa.name:
             p.unlink()
