@@ -131,6 +131,10 @@ class KmerCounter:
         """0 = automatic (pinned input -> device strip, pageable -> host strip threads), 1 = host loader, 2 = device loader."""
         self._check(self._lib.fkb_set_option(self._ctx, b"loader", int(mode)))
 
+    def set_loader_slots(self, n_slots: int) -> None:
+        """size of the host loader's ring of pinned 4 MiB slots (2..64; default 24)"""
+        self._check(self._lib.fkb_set_option(self._ctx, b"loader_slots", int(n_slots)))
+
     def set_loader_chunk(self, nbytes: int) -> None:
         self._check(self._lib.fkb_set_option(self._ctx, b"loader_chunk", int(nbytes)))
 

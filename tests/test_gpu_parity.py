@@ -385,6 +385,22 @@ def test_host_pipeline_multi_block_and_eof_alias(counter, harness):
     assert_counts_equal(counter.count_fasta(data, 10), want)
 
 
+def test_host_pipeline_ring_wraps_around(harness):
+    """more loader blocks than pinned slots: every slot is reused (a block may only be stripped into a slot whose previous
+    copy has been retired), with the count kernels issued per arrived piece; also the option's bounds"""
+    from findkmer_b200 import FindKmerError, synth
+    from findkmer_b200.engine import KmerCounter
+    data = synth.render(synth.config5(n_bases=30_000_000))  # 8 blocks of 4 MiB
+    want = harness.oracle_count_fasta(data, 9)
+    with KmerCounter(0) as c:
+        for bad in (1, 65):
+            with pytest.raises(FindKmerError):
+                c.set_loader_slots(bad)
+        for slots in (2, 3, 64):
+            c.set_loader_slots(slots)
+            assert_counts_equal(c.count_fasta(data, 9), want)
+
+
 def test_count_file_and_range_shards(counter, harness, tmp_path):
     from findkmer_b200 import synth
     data = synth.render(synth.config5(n_bases=3_000_000))
