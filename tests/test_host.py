@@ -82,6 +82,30 @@ def test_strip_dense_special_bytes(harness, strip_isa):
     assert compared >= 60
 
 
+def test_strip_property_any_bytes(harness, strip_isa):
+    """hypothesis: any byte string over a FASTA-flavoured alphabet strips exactly as the oracle's scan says, status included"""
+    from hypothesis import given, settings, strategies as st
+    from findkmer_b200 import FindKmerError, _lib
+    from findkmer_b200.engine import KmerCounter
+    status_of = {harness.FKO_ERR_EMPTY: _lib.FKB_ERR_EMPTY_INPUT, harness.FKO_ERR_UNTERMINATED_HDR: _lib.FKB_ERR_UNTERMINATED_HEADER}
+    piece = st.one_of(st.sampled_from([b"\n", b">", b"\xff", b"ACGT" * 20, b"N" * 70, b"acgtn", b">hdr \xff >\n", b"?~\x7f\xbe"]),
+                      st.binary(min_size=1, max_size=40))
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.lists(piece, min_size=0, max_size=30))
+    def check(pieces):
+        data = b"".join(pieces)
+        rc, want = harness.oracle_strip(data)
+        if rc == harness.FKO_OK:
+            assert bytes(KmerCounter.strip(data, 2)) == bytes(want)
+        else:
+            with pytest.raises(FindKmerError) as e:
+                KmerCounter.strip(data, 2)
+            assert e.value.status == status_of[rc]
+
+    check()
+
+
 def test_strip_matches_contract_on_golden_inputs(harness, golden, test_txt, strip_isa):
     from findkmer_b200 import FindKmerError, _lib
     from findkmer_b200.engine import KmerCounter
