@@ -31,7 +31,7 @@ EXPORTS = [
     "fkb_table_entries", "fkb_prefix_flags_bytes", "fkb_zero_device", "fkb_count_stream_device", "fkb_finalize_device",
     "fkb_count_fasta_host", "fkb_count_stream_host", "fkb_count_fasta_host_range", "fkb_count_file",
     "fkb_count_fasta_host_multi", "fkb_count_file_multi",
-    "fkb_write_base_stats", "fkb_write_histogram", "fkb_max_nodes",
+    "fkb_write_base_stats", "fkb_write_histogram", "fkb_write_histogram_tsv", "fkb_max_nodes",
     "fkb_synth_fasta_device", "fkb_launch_count",
 ]
 
@@ -128,6 +128,8 @@ def load() -> ctypes.CDLL:
     lib.fkb_write_histogram.argtypes = [c_void_p, c_int, c_void_p, POINTER(FkbCounts), POINTER(ctypes.c_longdouble * 4), c_int,
                                         ctypes.c_longdouble, c_int, POINTER(c_uint64)]
     lib.fkb_write_histogram.restype = c_int
+    lib.fkb_write_histogram_tsv.argtypes = lib.fkb_write_histogram.argtypes
+    lib.fkb_write_histogram_tsv.restype = c_int
     lib.fkb_max_nodes.argtypes = [c_int]
     lib.fkb_max_nodes.restype = c_uint64
     lib.fkb_synth_fasta_device.argtypes = [ctx, c_void_p, c_uint64, c_uint64, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,

@@ -14,10 +14,15 @@
 // invalid free() after closing its files, :1370-1371); a missing option value prints usage once and exits 1
 // instead of looping forever (:1302-1303); unknown characters are reported once with a count instead of one
 // stderr line each (:581-585); k = 17..20 is refused (dense 4^k tables); -K/--ksweep (several k in one run: the file is
-// uploaded and stripped once) and -g/--gpus are extensions.
+// uploaded and stripped once), -g/--gpus (contiguous shards of the file on several GPUs of this box) and -t/--tsv (the
+// histogram once more as the tab-separated table mergeFile4GNUPLOT.pl joins) are extensions.
+#include <fcntl.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <chrono>
 #include <string>
@@ -46,6 +51,7 @@ struct Config {
     long double z_threshold = -1;
     int gpus = 1;
     std::vector<int> sweep;  // -K/--ksweep a-b | a,b,c : several k in one run (extension; one upload, one strip)
+    std::string tsv_file;    // -t/--tsv <file>: tab-separated copy of the histogram for mergeFile4GNUPLOT.pl (extension)
 };
 
 void usage()
@@ -143,6 +149,10 @@ bool parse_arguments(int argc, char **argv, Config &cfg)
                     fprintf(stderr, "%d is not a valid value for k.\nPlease select a number greater than zero and less than %d\n", k, FKB_MAX_K + 1);
                     exit(EXIT_FAILURE);
                 }
+        } else if (!strcmp(a, "-t") || !strcmp(a, "--tsv")) {  // extension: the table mergeFile4GNUPLOT.pl joins
+            if (++i == argc) { fprintf(stderr, "TSV file name missing.\n"); return false; }
+            check_file(argv[i], "w");
+            cfg.tsv_file = argv[i];
         } else if (!strcmp(a, "-g") || !strcmp(a, "--gpus")) {  // extension
             if (++i == argc) { fprintf(stderr, "Number of GPUs is missing.\n"); return false; }
             cfg.gpus = atoi(argv[i]) > 0 ? atoi(argv[i]) : 1;
@@ -188,6 +198,46 @@ void print_memory_estimate(const Config &cfg)  // estimate_RAM_usage, :1256-1289
     } else {
         fprintf(stdout, "%g mibibytes of RAM usage likely\n", ram / mib);
     }
+}
+
+// The per-record progress lines of a non-quiet run (findKmer() :994-1003): at every '>' outside a header the reference
+// prints "Read <baseCounter> bases", then echoes the header line.  baseCounter at that moment is the number of bases in
+// runs of length >= k seen so far (:1040, :1056) -- a running sum over the file that the one-shot GPU count does not
+// produce, so this (and only this) is scanned on the host, and only when -q 0 asks for it; the k-mer table never is.
+void print_progress_lines(const char *path, int k)
+{
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size == 0) { close(fd); return; }
+    const size_t len = (size_t)st.st_size;
+    const unsigned char *buf = (const unsigned char *)mmap(nullptr, len, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (buf == MAP_FAILED) return;
+    unsigned long long base_counter = 0, run = 0;
+    for (size_t p = 0; p < len; ++p) {
+        const unsigned char c = buf[p];
+        if (c == 0xFF) break;  // fgetc() stored in a char: EOF alias (:975, :988)
+        if (c == '>') {
+            run = 0;
+            const unsigned char *nl = (const unsigned char *)memchr(buf + p, '\n', len - p);
+            const size_t e = nl ? (size_t)(nl - buf) : len;
+            fprintf(stdout, "Read %llu bases\n", base_counter);
+            fwrite(buf + p, 1, e - p, stdout);
+            fprintf(stdout, "\n");
+            p = e;  // the '\n' itself is ignored by the scan (:1011)
+            continue;
+        }
+        if (c == '\n') continue;
+        if (c == 'A' || c == 'C' || c == 'G' || c == 'T') {
+            ++run;
+            if (run > (unsigned long long)k) ++base_counter;            // :1040
+            else if (run == (unsigned long long)k) base_counter += k;   // :1056
+        } else {
+            run = 0;  // :1019-1024
+        }
+    }
+    munmap((void *)buf, len);
 }
 
 }  // namespace
@@ -256,6 +306,7 @@ int main(int argc, char **argv)
     fprintf(stdout, "!!!Find The KMER!!!\n");
     fprintf(stdout, "Reading sequence from file\n");
     fprintf(stdout, "     2858658142 bases in the reference genome FYI.\nThat is 2,858,658,142 by the way.\n");
+    if (cfg.suppress_output == 0) print_progress_lines(cfg.sequence_file.c_str(), cfg.k);  // :996-1002
     fflush(stdout);
 
     // ---- the counting path: findKmer() -> GPU ----
@@ -362,6 +413,16 @@ int main(int argc, char **argv)
             fprintf(stderr, "Out file write error! (%s)\n", fkb_status_string(status));
             fclose(csv);
             return EXIT_FAILURE;
+        }
+        if (!cfg.tsv_file.empty()) {  // extension: the same rows, tab-separated, for mergeFile4GNUPLOT.pl
+            const std::string tsv_name = ks.size() > 1 ? std::to_string(k) + "mer_" + cfg.tsv_file : cfg.tsv_file;
+            FILE *tsv = fopen(tsv_name.c_str(), "w");
+            uint64_t tsv_rows = 0;
+            if (!tsv || fkb_write_histogram_tsv(tsv, k, tables[i].data(), &counts, base_probability, cfg.z_enable, cfg.z_threshold, 0, &tsv_rows) != FKB_OK) {
+                fprintf(stderr, "TSV file write error!\n");
+                exit_code = EXIT_FAILURE;
+            }
+            if (tsv) fclose(tsv);
         }
         fprintf(stdout, "histogram creation finished.\n");
         if (fclose(csv) == EOF)

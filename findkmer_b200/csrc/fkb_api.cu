@@ -13,6 +13,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -128,8 +129,10 @@ int ensure_bucket_scratch(fkb_context *ctx, int k, uint64_t range_bytes)
     if (cap_front > 0x3FFFFFF8ull) cap_front = 0x3FFFFFF8ull;
     // back part = 50 % of the front part (2x the average fill: enough for buckets up to ~3.5x as popular as the average; beyond that
     // the surplus is escaped exactly).  A larger one costs ~1 % on evenly loaded input (regions further apart: TLB reach).
-    uint64_t back_percent = 50;  // FKB_BACK_PERCENT overrides (tuning knob)
-    if (const char *e = getenv("FKB_BACK_PERCENT")) back_percent = (uint64_t)atoi(e);
+    static const uint64_t back_percent = [] {  // FKB_BACK_PERCENT overrides (tuning knob, read once)
+        const char *e = getenv("FKB_BACK_PERCENT");
+        return e ? (uint64_t)atoi(e) : 50ull;
+    }();
     uint64_t cap = cap_front + ((cap_front * back_percent / 100 + 7) & ~7ull);
     if (!fkb::bucket_folds_in_shared(k)) {  // k <= 8 only: the 16-bit 13-mer table (128 MiB) and the fold levels
         if (!ctx->bucket.table_w) FKB_CUDA(ctx, cudaMalloc(&ctx->bucket.table_w, fkb::bucket_table_w_bytes()));
@@ -255,6 +258,8 @@ static int pipeline_range_device(fkb_context *ctx, const uint8_t *fasta, size_t 
     *stop_offset = UINT64_MAX;
     *ends_in_header_out = 0;
     if (int s = ensure_stream(ctx, (len - own_offset) + 16 + 64)) return s;
+    if (k)  // pieces of up to 96 MiB + one chunk are counted at a time
+        if (int s = ensure_bucket_scratch(ctx, k, std::min<uint64_t>(len - own_offset, (96ull << 20) + kRawChunkBytes))) return s;
     if (!ctx->d_raw[0]) {
         for (int i = 0; i < 2; ++i) {
             FKB_CUDA(ctx, cudaMalloc(&ctx->d_raw[i], kRawChunkBytes + 64));
@@ -340,6 +345,8 @@ static int pipeline_range(fkb_context *ctx, const uint8_t *fasta, size_t len, si
     *ends_in_header_out = 0;
     phase_mark("(enter pipeline)");
     if (int s = ensure_stream(ctx, (len - own_offset) + 16 + 64)) return s;
+    if (k)  // pieces of 32 MiB (+ one block) are counted at a time
+        if (int s = ensure_bucket_scratch(ctx, k, std::min<uint64_t>(len - own_offset, (32ull << 20) + kBlockBytes))) return s;
     phase_mark("device stream alloc");
     const size_t span = len - own_offset;
     const size_t n_blocks = (span + kBlockBytes - 1) / kBlockBytes;
@@ -356,6 +363,7 @@ static int pipeline_range(fkb_context *ctx, const uint8_t *fasta, size_t len, si
     if (n_threads >= 8 && !getenv("FKB_HOST_THREADS")) --n_threads;  // one core stays with the committing thread
     if ((size_t)n_threads > n_blocks) n_threads = (int)n_blocks;
 
+    const std::vector<uint8_t> hdr_state = fkb::header_states(fasta, own_offset, len, kBlockBytes, n_threads);
     struct Task { fkb::StripResult r; bool done = false; };
     std::vector<Task> tasks(n_blocks);
     std::mutex mu;
@@ -374,7 +382,7 @@ static int pipeline_range(fkb_context *ctx, const uint8_t *fasta, size_t len, si
                 if (abort_all) return;
             }
             size_t a = own_offset + i * kBlockBytes, b = a + kBlockBytes < len ? a + kBlockBytes : len;
-            fkb::StripResult r = fkb::strip_block(fasta, a, b, fkb::in_header_at(fasta, a), ctx->slots[i % n_slots]);
+            fkb::StripResult r = fkb::strip_block(fasta, a, b, hdr_state[i] != 0, ctx->slots[i % n_slots]);
             {
                 std::lock_guard<std::mutex> lk(mu);
                 tasks[i].r = r;
@@ -676,9 +684,10 @@ int fkb_strip_fasta(const uint8_t *fasta, size_t len, uint8_t *stream, size_t *s
         for (auto &th : pool) th.join();
     };
     // pass A: sizes
+    const std::vector<uint8_t> hdr_state = fkb::header_states(fasta, 0, len, kBlockBytes, n_threads);
     run_pass([&](size_t i) {
         size_t a = i * kBlockBytes, b = a + kBlockBytes < len ? a + kBlockBytes : len;
-        blocks[i].hdr = fkb::in_header_at(fasta, a);
+        blocks[i].hdr = hdr_state[i] != 0;
         blocks[i].r = fkb::strip_block_count(fasta, a, b, blocks[i].hdr);
     });
     size_t total = 0, last = n_blocks;  // `last`: block that holds the terminating 0xFF, if any
@@ -751,6 +760,7 @@ int fkb_count_stream_host(fkb_context *ctx, const uint8_t *stream, size_t len, i
     FKB_CUDA(ctx, cudaSetDevice(ctx->device));
     if (int s = ensure_table(ctx, k)) return s;
     if (int s = ensure_stream(ctx, len + 64)) return s;
+    if (int s = ensure_bucket_scratch(ctx, k, std::min<uint64_t>(len, 64ull << 20))) return s;
     if (int s = fkb_zero_device(ctx, k, ctx->d_table, ctx->d_flags, ctx->d_partials, ctx->s_pipe)) return s;
     // chunked so the count of chunk i overlaps the copy of chunk i+1 (copy engine vs SMs, one ordered stream
     // is enough: a kernel on [a,b) only needs bytes < b, and the copies are issued in order on a second stream)

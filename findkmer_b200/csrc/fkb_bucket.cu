@@ -27,6 +27,7 @@
 // layout answers (38 % of instructions in the flush copy loop, 15 % in run-mask loops, a barrier per iteration);
 // profiles/r01_ncu_full_summary.txt is where it stands: both passes bound by the shared-memory data pipe (bank
 // conflicts of random 32-lane accesses, 3.5 wavefronts per atomic / 16-bit store).
+#include <atomic>
 #include <type_traits>
 
 #include "fkb_kernels.cuh"
@@ -887,7 +888,7 @@ __global__ void __launch_bounds__(256) fold_level_kernel(const TIn *__restrict__
         }
         all += suf;
         if (table_k) {
-            if (all) table_k[y] += all;
+            if (all) red_add_u32(table_k + y, all);  // T_k is live: the edge slivers add to it concurrently on the side stream
         } else {
             all_out[y] = all;
             suf_out[y] = suf;
@@ -899,7 +900,7 @@ __global__ void __launch_bounds__(256) fold_copy_kernel(const uint16_t *__restri
 {
     for (uint64_t x = (uint64_t)blockIdx.x * 256 + threadIdx.x; x < n; x += (uint64_t)gridDim.x * 256) {
         const uint32_t v = table_w[x];
-        if (v) table_k[x] += v;
+        if (v) red_add_u32(table_k + x, v);  // T_k is live (edge slivers on the side stream)
     }
 }
 
@@ -941,13 +942,19 @@ template <int S>
 cudaError_t run_bucketed(const LaunchInfo &li, const BucketScratch &bs, const uint8_t *d_stream, uint64_t lo, uint64_t hi,
                          uint32_t *d_table, uint8_t *d_flags, fkb_partials *d_partials, cudaStream_t st, int *launches)
 {
-    static bool attr_done = false;
-    if (!attr_done) {
+    // the dynamic shared-memory opt-in is a PER-DEVICE function attribute: remembered per device (one bit each), so that
+    // contexts on several GPUs of one process (findKmer -g N) all get it
+    static std::atomic<uint64_t> attr_done{0};
+    int dev = 0;
+    cudaError_t ed = cudaGetDevice(&dev);
+    if (ed != cudaSuccess) return ed;
+    const uint64_t dev_bit = 1ull << (dev & 63);
+    if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
         cudaError_t e = cudaFuncSetAttribute(bucketize_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P1Smem));
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(count_buckets_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done.fetch_or(dev_bit, std::memory_order_release);
     }
     const uint64_t wspan = 32ull * 16 * S;
     const uint64_t n_witers = (hi - lo) / wspan;

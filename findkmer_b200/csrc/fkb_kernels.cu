@@ -467,6 +467,7 @@ cudaError_t launch_count(const LaunchInfo &li, const uint8_t *d_stream, uint64_t
     if (end <= begin) return cudaSuccess;
     const uint64_t unit = bucket_unit_bytes(k);
     bool bucket = unit && li.bucket.gbuf && li.variant != VARIANT_DIRECT;
+    if (bucket && !bucket_folds_in_shared(k) && !(li.bucket.table_w && li.bucket.fold)) bucket = false;  // k <= 8 needs the W-mer table and the fold scratch
     uint64_t lo = 0, hi = 0;
     if (bucket) {
         // interior [lo, hi): whole units, aligned in absolute stream coordinates, 16 readable bytes on both sides

@@ -9,6 +9,7 @@
 // Every other byte is copied verbatim; the device decides what is a base.
 #include "fkb_loader.h"
 
+#include <stdlib.h>
 #include <string.h>
 #include <thread>
 
@@ -31,6 +32,37 @@ bool in_header_at(const uint8_t *buf, size_t pos)
     const uint8_t *nl = (const uint8_t *)memrchr(buf, '\n', pos);
     size_t line_start = nl ? (size_t)(nl - buf) + 1 : 0;
     return memchr(buf + line_start, '>', pos - line_start) != nullptr;
+}
+
+// Header state at every block start first + i * block_bytes (i < n_blocks) of buf[first, len).
+// One look-back for block 0; every later state follows from a summary of the block in front of it -- does it hold a '\n',
+// and is there a '>' after its last '\n' (or anywhere, when it has none) -- combined in order.  Each byte is looked at by at
+// most one memrchr and one memchr: an unwrapped record (one line of 100 MB and more) costs one pass over the file here
+// instead of one look-back over the whole line per block.
+std::vector<uint8_t> header_states(const uint8_t *buf, size_t first, size_t len, size_t block_bytes, int n_threads)
+{
+    const size_t n_blocks = len > first ? (len - first + block_bytes - 1) / block_bytes : 0;
+    std::vector<uint8_t> state(n_blocks ? n_blocks : 1, 0);
+    if (!n_blocks) return state;
+    std::vector<uint8_t> summary(n_blocks, 0);  // bit 0: the block holds a '\n'; bit 1: a '>' after its last '\n' (or anywhere, when none)
+    auto summarise = [&](size_t i) {
+        const size_t a = first + i * block_bytes, b = a + block_bytes < len ? a + block_bytes : len;
+        const uint8_t *nl = (const uint8_t *)memrchr(buf + a, '\n', b - a);
+        const size_t from = nl ? (size_t)(nl - buf) + 1 : a;
+        summary[i] = (uint8_t)((nl ? 1 : 0) | (memchr(buf + from, '>', b - from) ? 2 : 0));
+    };
+    if (n_threads > 1 && n_blocks >= 64) {
+        std::vector<std::thread> pool;
+        const int nt = (int)((size_t)n_threads < n_blocks / 16 ? (size_t)n_threads : n_blocks / 16);
+        for (int t = 0; t < nt; ++t)
+            pool.emplace_back([&, t] { for (size_t i = (size_t)t; i + 1 < n_blocks; i += (size_t)nt) summarise(i); });
+        for (auto &th : pool) th.join();
+    } else {
+        for (size_t i = 0; i + 1 < n_blocks; ++i) summarise(i);
+    }
+    state[0] = in_header_at(buf, first) ? 1 : 0;
+    for (size_t i = 0; i + 1 < n_blocks; ++i) state[i + 1] = (summary[i] & 1) ? (summary[i] >> 1) : (uint8_t)(state[i] | (summary[i] >> 1));
+    return state;
 }
 
 namespace {

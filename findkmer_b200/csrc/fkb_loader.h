@@ -5,6 +5,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <vector>
+
 namespace fkb {
 
 struct StripResult {
@@ -15,6 +17,9 @@ struct StripResult {
 
 // True iff position `pos` of buf lies inside a '>' header line (a '>' occurs between the previous '\n' and pos).
 bool in_header_at(const uint8_t *buf, size_t pos);
+
+// in_header_at() for every block start first + i * block_bytes of buf[first, len), in one bounded pass (see fkb_loader.cpp)
+std::vector<uint8_t> header_states(const uint8_t *buf, size_t first, size_t len, size_t block_bytes, int n_threads);
 
 // Strip buf[a,b) into out (room for b-a bytes).  `in_header`: state at a (from in_header_at).
 // Stops at the first 0xFF outside a header.

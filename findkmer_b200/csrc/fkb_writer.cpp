@@ -143,8 +143,10 @@ struct TailCache {
 };
 
 // format the rows of table[lo, hi) into out
+// tsv: the same row as `kmer \t h \t frequency \t H [\t z] \n` -- tab-separated with the count in column 2, the layout
+// mergeFile4GNUPLOT.pl joins on (it splits on tabs, keys on column 0 and carries columns 1 and 2, :13-32)
 void format_slice(const uint32_t *table, uint64_t lo, uint64_t hi, int k, const CompositionTable &ct, int z_enable, long double z_thr,
-                  std::string &out, uint64_t &rows, TailCache &cache)
+                  std::string &out, uint64_t &rows, TailCache &cache, bool tsv)
 {
     static const char letters[4] = {'A', 'C', 'G', 'T'};
     const uint32_t lo_bits = 0x55555555u;
@@ -180,16 +182,37 @@ void format_slice(const uint32_t *table, uint64_t lo, uint64_t hi, int k, const 
         n += cp.text_len;
         memcpy(row + n, te.text, te.len);
         n += te.len;
-        out.append(row, (size_t)n);
+        if (tsv) {
+            // row = '\n' kmer ", " h ", " H ", " freq [", " z]: same text, fields re-ordered and tab-separated
+            const char *f[5];
+            int fl[5], nf = 0;
+            const char *p = row + 1, *end = row + n;
+            while (nf < 5) {
+                const char *q = p;
+                while (q + 1 < end && !(q[0] == ',' && q[1] == ' ')) ++q;
+                const bool last = q + 1 >= end;
+                f[nf] = p;
+                fl[nf++] = (int)((last ? end : q) - p);
+                if (last) break;
+                p = q + 2;
+            }
+            static const int order[5] = {0, 1, 3, 2, 4};
+            for (int i = 0; i < nf; ++i) {
+                if (i) out.push_back('\t');
+                out.append(f[order[i]], (size_t)fl[order[i]]);
+            }
+            out.push_back('\n');
+        } else {
+            out.append(row, (size_t)n);
+        }
         ++rows;
     }
 }
 
 }  // namespace
 
-extern "C" int fkb_write_histogram(FILE *csv_out, int k, const uint32_t *table, const fkb_counts *counts,
-                                   const long double base_probability[4], int z_threshold_enable, long double z_threshold, int n_threads,
-                                   uint64_t *rows_written)
+static int write_histogram_impl(FILE *csv_out, int k, const uint32_t *table, const fkb_counts *counts, const long double base_probability[4],
+                                int z_threshold_enable, long double z_threshold, int n_threads, uint64_t *rows_written, bool tsv)
 {
     if (!csv_out || !table || !counts || !base_probability || k < 1 || k > FKB_MAX_K) return FKB_ERR_BAD_ARG;
     if (rows_written) *rows_written = 0;
@@ -227,7 +250,7 @@ extern "C" int fkb_write_histogram(FILE *csv_out, int k, const uint32_t *table, 
             }
             std::string &b = bufs[s % ring];
             b.clear();
-            format_slice(table, s * slice, (s + 1) * slice, k, ct, z_threshold_enable, z_threshold, b, rows[s], caches[(size_t)t]);
+            format_slice(table, s * slice, (s + 1) * slice, k, ct, z_threshold_enable, z_threshold, b, rows[s], caches[(size_t)t], tsv);
             {
                 std::lock_guard<std::mutex> lk(mu);
                 done[s] = 1;
@@ -259,4 +282,18 @@ extern "C" int fkb_write_histogram(FILE *csv_out, int k, const uint32_t *table, 
     if (status != FKB_OK) return status;
     if (rows_written) *rows_written = total_rows;
     return FKB_OK;
+}
+
+extern "C" int fkb_write_histogram(FILE *csv_out, int k, const uint32_t *table, const fkb_counts *counts,
+                                   const long double base_probability[4], int z_threshold_enable, long double z_threshold, int n_threads,
+                                   uint64_t *rows_written)
+{
+    return write_histogram_impl(csv_out, k, table, counts, base_probability, z_threshold_enable, z_threshold, n_threads, rows_written, false);
+}
+
+extern "C" int fkb_write_histogram_tsv(FILE *tsv_out, int k, const uint32_t *table, const fkb_counts *counts,
+                                       const long double base_probability[4], int z_threshold_enable, long double z_threshold, int n_threads,
+                                       uint64_t *rows_written)
+{
+    return write_histogram_impl(tsv_out, k, table, counts, base_probability, z_threshold_enable, z_threshold, n_threads, rows_written, true);
 }

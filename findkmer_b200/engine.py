@@ -284,16 +284,18 @@ CSV_HEADER = b"Sequence, Shannon Entropy h, Shannon Entropy H, Frequency, Z scor
 
 
 def write_outputs(counts: KmerCounts, csv_path: str, stats_path: str, z_threshold: Optional[int] = None,
-                  console_path: Optional[str] = None, n_threads: int = 0) -> int:
+                  console_path: Optional[str] = None, n_threads: int = 0, tsv_path: Optional[str] = None) -> int:
     """Write <k>mer_Historam_Of_<file>.csv and <k>mer_Base_Stats_Of_<file>.txt byte-identically to the reference.
-    Returns the FKB status (FKB_ERR_ZERO_BASE_PROBABILITY leaves a header-only CSV, as the reference does)."""
+    Returns the FKB status (FKB_ERR_ZERO_BASE_PROBABILITY leaves a header-only CSV, as the reference does).
+    tsv_path: additionally the tab-separated table mergeFile4GNUPLOT.pl joins (kmer, h, frequency, H[, z])."""
     lib = _lib.load()
     c = _c()
     raw = counts.raw
     csv = c.fopen(str(csv_path).encode(), b"w")
     stats = c.fopen(str(stats_path).encode(), b"w")
     console = c.fopen(str(console_path).encode(), b"w") if console_path else None
-    if not csv or not stats:
+    tsv = c.fopen(str(tsv_path).encode(), b"w") if tsv_path else None
+    if not csv or not stats or (tsv_path and not tsv):
         raise OSError("cannot open output files")
     try:
         c.fputs(CSV_HEADER, csv)
@@ -306,9 +308,16 @@ def write_outputs(counts: KmerCounts, csv_path: str, stats_path: str, z_threshol
                                              1 if z_threshold is not None else 0,
                                              ctypes.c_longdouble(float(z_threshold) if z_threshold is not None else 1000.0),
                                              n_threads, ctypes.byref(rows))
+            if status == _lib.FKB_OK and tsv:
+                status = lib.fkb_write_histogram_tsv(tsv, counts.k, table.ctypes.data, ctypes.byref(raw), ctypes.byref(probs),
+                                                     1 if z_threshold is not None else 0,
+                                                     ctypes.c_longdouble(float(z_threshold) if z_threshold is not None else 1000.0),
+                                                     n_threads, ctypes.byref(rows))
         return status
     finally:
         c.fclose(csv)
         c.fclose(stats)
+        if tsv:
+            c.fclose(tsv)
         if console:
             c.fclose(console)

@@ -167,6 +167,12 @@ int fkb_write_base_stats(FILE *stats_out, FILE *console, int k, const fkb_counts
 int fkb_write_histogram(FILE *csv_out, int k, const uint32_t *table, const fkb_counts *counts,
                         const long double base_probability[4], int z_threshold_enable, long double z_threshold,
                         int n_threads, uint64_t *rows_written);
+/* The same rows for mergeFile4GNUPLOT.pl (findKmer/mergeFile4GNUPLOT.pl:13-32 joins two TAB-separated tables on column 0 and
+ * carries columns 1 and 2): one line per observed k-mer, `kmer \t h \t frequency \t H [\t z] \n`, no header line, same
+ * row order, same number formats and same Z-score filter as fkb_write_histogram.  An extension: the reference writes CSV only. */
+int fkb_write_histogram_tsv(FILE *tsv_out, int k, const uint32_t *table, const fkb_counts *counts,
+                            const long double base_probability[4], int z_threshold_enable, long double z_threshold,
+                            int n_threads, uint64_t *rows_written);
 uint64_t fkb_max_nodes(int k);
 
 /* ---- synthetic inputs of the BASELINE.json shapes, generated in HBM (bench only) --------------

@@ -461,6 +461,91 @@ def test_full_size_properties(counter):
     torch.cuda.empty_cache()
 
 
+@pytest.mark.parametrize("name,k", [("config4", 11), ("config5", 8), ("config5", 11), ("config4", 8)])
+def test_full_size_against_golden(counter, name, k):
+    """BASELINE.json configs 4 and 5 at their FULL size (3.1e9 bases) against the oracle: tests/golden/golden_fullsize.json
+    holds sha256(table) and the scalars of a record-parallel run of the C restatement (make_golden_fullsize.py, ~4 min on
+    8 cores).  The input is rendered on the device by the bit-identical CUDA twin of synth.py."""
+    import hashlib
+    import json
+    import torch
+    from conftest import GOLDEN_DIR
+    from findkmer_b200 import synth
+    want = json.loads((GOLDEN_DIR / "golden_fullsize.json").read_text())["records"][f"{name}_k{k}"]
+    lay = getattr(synth, name)()
+    assert (lay.n_bases, lay.n_records, lay.seed) == (want["n_bases"], want["n_records"], want["seed"])
+    d = counter.synth_fasta_device(lay.stripped())
+    acc = counter.new_accumulators(k)
+    counter.count_stream_device(d, k, acc)
+    got = counter.finalize_device(acc, d.numel())
+    assert got.n_kmers == want["n_kmers"] and got.base_total == want["base_total"]
+    assert list(got.base_count) == want["base_count"]
+    assert got.node_count == want["node_count"] and got.unknown_chars == want["unknown_chars"]
+    assert {str(i): int(got.table[i]) for i in (0, 1, 4 ** k // 3, 4 ** k - 1)} == want["spot"]
+    assert hashlib.sha256(np.ascontiguousarray(got.table, dtype="<u4").tobytes()).hexdigest() == want["table_sha256"]
+    del d, acc
+    torch.cuda.empty_cache()
+
+
+def test_counter_rollover_is_reported(counter):
+    """findKmer.cpp:640-648: a trie node visited 2^32 times ends the reference with COUNTER ROLLOVER DETECTED.  Three poly-A
+    records of 1.5e9 bases (each below 2^31: the reference's seqSize is an int) visit the depth-1 node 'A' 4.5e9 times and
+    wrap table[AAAAAA]: the library must say FKB_ERR_COUNTER_ROLLOVER through finalize, whichever count path ran."""
+    import torch
+    from findkmer_b200._lib import FKB_ERR_COUNTER_ROLLOVER, FindKmerError
+    n_rec, rec = 3, 1_500_000_000
+    d = torch.full((n_rec * (rec + 1),), ord("A"), dtype=torch.uint8, device="cuda:0")
+    d[:: rec + 1] = ord(">")
+    k = 6
+    for variant in (0, 1):
+        counter.set_variant(variant)
+        try:
+            acc = counter.new_accumulators(k)
+            counter.count_stream_device(d, k, acc)
+            with pytest.raises(FindKmerError) as e:
+                counter.finalize_device(acc, d.numel())
+            assert e.value.status == FKB_ERR_COUNTER_ROLLOVER
+            # the wrapped bin holds the count modulo 2^32, as the reference's unsigned would have
+            assert int(acc.table[0].item()) & 0xFFFFFFFF == (n_rec * (rec - k + 1)) % (1 << 32)
+        finally:
+            counter.set_variant(0)
+    # just below the limit nothing is reported: 2 records of 2^31 - 8 bases = 2^32 - 16 visits
+    rec2 = (1 << 31) - 8
+    d2 = d[: 2 * (rec2 + 1)]
+    d2[:] = ord("A")
+    d2[:: rec2 + 1] = ord(">")
+    d2[5] = ord("C"); d2[6] = ord("G"); d2[7] = ord("T")  # noqa: E702  (all four bases occur)
+    acc = counter.new_accumulators(k)
+    counter.count_stream_device(d2, k, acc)
+    ok = counter.finalize_device(acc, d2.numel())
+    assert ok.n_kmers == 2 * (rec2 - k + 1)
+    del d, d2, acc
+    torch.cuda.empty_cache()
+
+
+def test_fresh_context_host_paths_after_a_large_device_count(harness):
+    """a context whose bucket scratch was sized by a k = 11 device count must not run the k <= 8 bucketed kernels
+    without their W-mer table / fold scratch when a HOST entry point is used next (and must size the scratch itself)."""
+    import torch
+    from findkmer_b200 import synth
+    from findkmer_b200.engine import KmerCounter
+    with KmerCounter(0) as c:
+        lay = synth.config4(n_bases=80_000_000).stripped()
+        d = c.synth_fasta_device(lay)
+        acc = c.new_accumulators(11)
+        c.count_stream_device(d, 11, acc)
+        c.finalize_device(acc, d.numel())
+        stream = d.cpu().numpy()
+        del d
+        for k in (8, 7):
+            got = c.count_stream(stream, k)   # 64 MiB chunks: above the k = 8 crossover
+            sub = stream[: 6_000_000]
+            assert np.array_equal(c.count_stream(sub, k).table, harness.oracle_count_stream(sub, k).table)
+            expect = sum(max(0, lay.record_bases(r) - k + 1) for r in range(lay.n_records))
+            assert got.n_kmers == expect == int(got.table.sum(dtype=np.uint64))
+    torch.cuda.empty_cache()
+
+
 def test_large_soft_masked_bucketed_equals_direct(counter):
     """1 Gbp of the config-5 shape (N runs + soft-masked runs: a run boundary in most warp iterations, so the general path of
     pass 1 -- masks, warp-cooperative run events, junk-cursor atomics, re-read on leaving a clean stretch -- carries the load):
@@ -509,10 +594,16 @@ def test_cli_binary_is_a_drop_in(harness, tmp_path):
         if z is not None:
             argv += ["-z", str(z)]
         if export:
-            argv += ["-e", export]
+            argv += ["-e", export, "-t", "mine.tsv"]
         run = subprocess.run(argv, cwd=work, capture_output=True, text=True, timeout=300)
         assert run.returncode == 0, run.stderr[-500:]
         assert (work / ref.csv_name).read_bytes() == ref.csv
+        if export:  # --tsv extension: the CSV's rows, tab-separated with the count in column 2 (mergeFile4GNUPLOT.pl's layout)
+            rows = ref.csv.split(b"\n")[1:]
+            lines = (work / "mine.tsv").read_bytes().split(b"\n")
+            assert len(lines) - 1 == len(rows) and lines[-1] == b""
+            f = rows[len(rows) // 2].split(b", ")
+            assert lines[len(rows) // 2].split(b"\t") == [f[0], f[1], f[3], f[2]] + f[4:]
         assert (work / ref.stats_name).read_bytes() == ref.stats
         # the stdout lines scripts may grep (the reference prints them too)
         for phrase in ("ATTEMPTING CONFIGURATION", "!!!Find The KMER!!!", "Reading sequence from file", "Statistics of occurrences",

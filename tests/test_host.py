@@ -211,6 +211,93 @@ def test_writer_live_against_reference_binary(harness, tmp_path):
         assert csv.read_bytes() == r.csv and stats.read_bytes() == r.stats
 
 
+def _tsv_join(path1, path2):
+    """What findKmer/mergeFile4GNUPLOT.pl:13-32 is meant to do: split both files on tabs, key on column 0, and for keys in
+    both emit  col0 \t col1(file1) \t col2(file1) \t col2(file2)."""
+    first = {}
+    for ln in open(path1, "rb").read().split(b"\n"):
+        f = ln.split(b"\t")
+        if len(f) >= 3:
+            first[f[0]] = (f[1], f[2])
+    out = {}
+    for ln in open(path2, "rb").read().split(b"\n"):
+        f = ln.split(b"\t")
+        if len(f) >= 3 and f[0] in first:
+            out[f[0]] = b"\t".join((f[0],) + first[f[0]] + (f[2],))
+    return out
+
+
+def test_tsv_export_feeds_the_gnuplot_join(harness, test_txt, tmp_path):
+    """the histogram once more as the tab-separated table mergeFile4GNUPLOT.pl joins (kmer, h, frequency, ...).
+    Two inputs (the launcher's upstream-vs-full comparison in miniature) -> two TSVs -> the join: every k-mer present in both
+    comes out with both counts, and the TSV rows are the CSV rows re-ordered (same text, so the same numbers)."""
+    import shutil
+    import subprocess
+    from findkmer_b200 import synth
+    from findkmer_b200.engine import write_outputs
+    k = 6
+    inputs = [test_txt, synth.render(synth.config3(n_records=40)).tobytes()]
+    tables = []
+    for i, data in enumerate(inputs):
+        o = harness.oracle_count_fasta(data, k)
+        kc = _counts_from_oracle(o, k)
+        csv, stats, tsv = tmp_path / f"{i}.csv", tmp_path / f"{i}.txt", tmp_path / f"{i}.tsv"
+        assert write_outputs(kc, csv, stats, tsv_path=tsv, n_threads=2) == 0
+        rows = csv.read_bytes().split(b"\n")[1:]
+        lines = tsv.read_bytes().split(b"\n")
+        assert lines[-1] == b"" and len(lines) - 1 == len(rows) == int(np.count_nonzero(o.table))
+        for row, line in zip(rows, lines):
+            f = row.split(b", ")
+            assert line.split(b"\t") == [f[0], f[1], f[3], f[2]] + f[4:]
+        tables.append(o.table)
+    joined = _tsv_join(tmp_path / "0.tsv", tmp_path / "1.tsv")
+    both = np.flatnonzero((tables[0] != 0) & (tables[1] != 0))
+    assert len(joined) == len(both) > 100
+    for code in both[:: max(1, len(both) // 50)]:
+        kmer = harness.code_to_kmer(int(code), k).encode()
+        f = joined[kmer].split(b"\t")
+        assert (int(f[2]), int(f[3])) == (int(tables[0][code]), int(tables[1][code]))
+    # where the reference tree and perl exist (this container, not the GPU box): the reference's own script with its two
+    # typos repaired on the fly (`split(/\t/. $line)` -> `,`; out-file argument index 3 -> 2) gives the same table
+    script = Path("/root/reference/findKmer/mergeFile4GNUPLOT.pl")
+    if script.exists() and shutil.which("perl"):
+        fixed = script.read_text().replace("split(/\\t/. $line)", "split(/\\t/, $line)").replace("$ARGV[3]", "$ARGV[2]")
+        (tmp_path / "merge_fixed.pl").write_text(fixed)
+        subprocess.run(["perl", "merge_fixed.pl", "0.tsv", "1.tsv", "merged.dat"], cwd=tmp_path, check=True, timeout=60)
+        got = {ln.split(b"\t")[0]: ln for ln in (tmp_path / "merged.dat").read_bytes().split(b"\n") if ln}
+        assert got == joined
+
+
+def test_cli_progress_lines_of_a_non_quiet_run(harness, test_txt, tmp_path):
+    """-q 0: `Read <baseCounter> bases` + the echoed header line at every record (findKmer.cpp:996-1002), byte for byte
+    against the untouched reference on its own fixture.  The lines are printed before the GPU is touched, so this runs
+    without one (the program then stops with its no-GPU message; on a GPU box it simply carries on)."""
+    import subprocess
+    exe = ROOT / "findkmer_b200" / "bin" / "findKmer"
+    if not exe.exists() or not harness.reference_available():
+        pytest.skip("CLI or reference binary not built")
+
+    def segment(text):
+        a = text.index("!!!Find The KMER!!!")
+        b = text.find("Statistics of occurrences", a)
+        return text[a:b] if b >= 0 else text[a:]
+
+    for k in (6, 11):
+        ref = harness.run_reference(test_txt, k, name="test.txt", probe=False)
+        work = tmp_path / f"q0_{k}"
+        work.mkdir()
+        (work / "test.txt").write_bytes(test_txt)
+        mine = subprocess.run([str(exe), "-q", "0", "-k", str(k), "-p", "test.txt"], cwd=work, capture_output=True, text=True,
+                              stdin=subprocess.DEVNULL, timeout=300)
+        quiet_ref = segment(ref.stdout)
+        assert "Read " not in quiet_ref  # harness runs the reference with -q 1
+        r0 = subprocess.run([str(harness.REF_BIN), "-q", "0", "-k", str(k), "-p", "test.txt"], cwd=work, capture_output=True, text=True,
+                            stdin=subprocess.DEVNULL, timeout=60)
+        want = segment(r0.stdout)
+        assert want.count("Read ") == 6 and ">ENST00000019317" in want
+        assert segment(mine.stdout) == want
+
+
 # ---- synthetic inputs -----------------------------------------------------------------------------------
 def test_synth_layouts_are_deterministic_and_shaped():
     from findkmer_b200 import synth
