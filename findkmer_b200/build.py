@@ -29,7 +29,7 @@ NVCC_FLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-
 # the writer must not be compiled with fast-math or FMA contraction: its output is compared byte for byte
 CXX_FLAGS = ["-O2", "-fPIC", "-std=c++17", "-Wall", "-Wextra", "-ffp-contract=off", "-I", str(ROOT / "include"), "-I", str(CSRC)]
 
-CU_SOURCES = ["fkb_kernels.cu", "fkb_bucket.cu", "fkb_strip.cu", "fkb_api.cu"]
+CU_SOURCES = ["fkb_kernels.cu", "fkb_bucket.cu", "fkb_smallk.cu", "fkb_strip.cu", "fkb_api.cu"]
 CXX_SOURCES = ["fkb_loader.cpp", "fkb_writer.cpp"]
 
 

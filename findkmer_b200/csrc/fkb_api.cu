@@ -118,7 +118,8 @@ void phase_mark(const char *what)
 int ensure_bucket_scratch(fkb_context *ctx, int k, uint64_t range_bytes)
 {
     const int S = fkb::bucket_stride_for(k);
-    if (!S || ctx->forced_variant == fkb::VARIANT_DIRECT) return FKB_OK;
+    if (!S || ctx->forced_variant == fkb::VARIANT_DIRECT || ctx->forced_variant == fkb::VARIANT_SMEM) return FKB_OK;
+    if (k <= 8 && ctx->forced_variant != fkb::VARIANT_BUCKET) return FKB_OK;  // k <= 8 takes the single-pass shared-memory path (fkb_smallk.cu)
     if (range_bytes < fkb::bucket_min_bytes(k) && ctx->forced_variant != fkb::VARIANT_BUCKET) return FKB_OK;  // the direct kernel will run
     const uint64_t items = range_bytes / S + 1;
     const uint64_t nb = (uint64_t)fkb::bucket_count(), n_cta = (uint64_t)ctx->sm_count;
@@ -599,7 +600,7 @@ int fkb_device_info(fkb_context *ctx, int *sm_count, int *cc_major, int *cc_mino
 int fkb_set_option(fkb_context *ctx, const char *name, long value)
 {
     if (!ctx || !name) return FKB_ERR_BAD_ARG;
-    if (!strcmp(name, "variant") && value >= 0 && value <= 2) {
+    if (!strcmp(name, "variant") && value >= 0 && value <= 3) {
         ctx->forced_variant = (int)value;
         return FKB_OK;
     }

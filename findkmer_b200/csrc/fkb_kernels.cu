@@ -461,29 +461,17 @@ uint64_t bucket_min_bytes(int k)
     return 22ull << 20;
 }
 
-cudaError_t launch_count(const LaunchInfo &li, const uint8_t *d_stream, uint64_t begin, uint64_t end, int k, uint32_t *d_table,
-                         uint8_t *d_flags, fkb_partials *d_partials, cudaStream_t st, int *launches)
+// The two edge slivers of an interior [lo, hi) go through the direct kernel (it owns every ragged / unaligned / short-halo
+// case), in one launch -- on a side stream forked here and joined at the end, so that its ~25 us of latency-bound work
+// hides behind the big kernels instead of standing in front of them (2 % of a 3.1 Gbp step, 10 % of a 1/8 shard).
+template <typename Interior>
+static cudaError_t launch_with_slivers(const LaunchInfo &li, const uint8_t *d_stream, uint64_t begin, uint64_t lo, uint64_t hi, uint64_t end, int k,
+                                       uint32_t *d_table, uint8_t *d_flags, fkb_partials *d_partials, cudaStream_t st, int *launches, Interior interior)
 {
-    if (end <= begin) return cudaSuccess;
-    const uint64_t unit = bucket_unit_bytes(k);
-    bool bucket = unit && li.bucket.gbuf && li.variant != VARIANT_DIRECT;
-    if (bucket && !bucket_folds_in_shared(k) && !(li.bucket.table_w && li.bucket.fold)) bucket = false;  // k <= 8 needs the W-mer table and the fold scratch
-    uint64_t lo = 0, hi = 0;
-    if (bucket) {
-        // interior [lo, hi): whole units, aligned in absolute stream coordinates, 16 readable bytes on both sides
-        lo = (begin + 16 + unit - 1) / unit * unit;
-        hi = end >= 16 ? (end - 16) / unit * unit : 0;
-        const uint64_t min_bytes = li.variant == VARIANT_BUCKET ? unit : bucket_min_bytes(k);
-        bucket = hi > lo && hi - lo >= min_bytes;
-    }
-    if (!bucket) return launch_direct(li, d_stream, begin, end, 0, 0, k, d_table, d_flags, d_partials, st, launches);
-    // The two edge slivers go through the direct kernel (it owns every ragged / unaligned / short-halo case), in one launch --
-    // on a side stream forked here and joined at the end, so that its ~25 us of latency-bound work hides behind pass 2
-    // instead of standing in front of pass 1 (2 % of a 3.1 Gbp step, 10 % of a 1/8 shard).
     if (li.edge_stream) {
         cudaError_t e = cudaEventRecord(li.edge_fork, st);  // the slivers depend on what precedes this call (zeroing), not on the big kernels
         if (e != cudaSuccess) return e;
-        e = launch_count_bucketed(li, li.bucket, d_stream, lo, hi, k, d_table, d_flags, d_partials, st, launches);
+        e = interior();
         if (e != cudaSuccess) return e;
         e = cudaStreamWaitEvent(li.edge_stream, li.edge_fork, 0);
         if (e != cudaSuccess) return e;
@@ -495,7 +483,39 @@ cudaError_t launch_count(const LaunchInfo &li, const uint8_t *d_stream, uint64_t
     }
     cudaError_t e = launch_direct(li, d_stream, begin, lo, hi, end, k, d_table, d_flags, d_partials, st, launches, true);
     if (e != cudaSuccess) return e;
-    return launch_count_bucketed(li, li.bucket, d_stream, lo, hi, k, d_table, d_flags, d_partials, st, launches);
+    return interior();
+}
+
+// Below this many interior bytes the single-pass shared-memory path (k <= 8) loses against the direct kernel: every CTA zeroes
+// and finally adds a whole 4^k table.
+uint64_t smallk_min_bytes(int k) { return k <= 6 ? (256ull << 10) : (512ull << 10); }
+
+cudaError_t launch_count(const LaunchInfo &li, const uint8_t *d_stream, uint64_t begin, uint64_t end, int k, uint32_t *d_table,
+                         uint8_t *d_flags, fkb_partials *d_partials, cudaStream_t st, int *launches)
+{
+    if (end <= begin) return cudaSuccess;
+    // k <= 8: single pass with the whole table in shared memory (AUTO), unless the bucketed / direct kernels are forced
+    if (const uint64_t unit = smallk_unit_bytes(k); unit && (li.variant == VARIANT_AUTO || li.variant == VARIANT_SMEM)) {
+        const uint64_t lo = (begin + 16 + unit - 1) / unit * unit, hi = end / unit * unit;
+        if (hi > lo && hi - lo >= (li.variant == VARIANT_SMEM ? unit : smallk_min_bytes(k)))
+            return launch_with_slivers(li, d_stream, begin, lo, hi, end, k, d_table, d_flags, d_partials, st, launches,
+                                       [&] { return launch_count_smallk(li, d_stream, lo, hi, k, d_table, d_flags, d_partials, st, launches); });
+        return launch_direct(li, d_stream, begin, end, 0, 0, k, d_table, d_flags, d_partials, st, launches);
+    }
+    const uint64_t unit = bucket_unit_bytes(k);
+    bool bucket = unit && li.bucket.gbuf && li.variant != VARIANT_DIRECT && li.variant != VARIANT_SMEM;
+    if (bucket && !bucket_folds_in_shared(k) && !(li.bucket.table_w && li.bucket.fold)) bucket = false;  // k <= 8 needs the W-mer table and the fold scratch
+    uint64_t lo = 0, hi = 0;
+    if (bucket) {
+        // interior [lo, hi): whole units, aligned in absolute stream coordinates, 16 readable bytes on both sides
+        lo = (begin + 16 + unit - 1) / unit * unit;
+        hi = end >= 16 ? (end - 16) / unit * unit : 0;
+        const uint64_t min_bytes = li.variant == VARIANT_BUCKET ? unit : bucket_min_bytes(k);
+        bucket = hi > lo && hi - lo >= min_bytes;
+    }
+    if (!bucket) return launch_direct(li, d_stream, begin, end, 0, 0, k, d_table, d_flags, d_partials, st, launches);
+    return launch_with_slivers(li, d_stream, begin, lo, hi, end, k, d_table, d_flags, d_partials, st, launches,
+                               [&] { return launch_count_bucketed(li, li.bucket, d_stream, lo, hi, k, d_table, d_flags, d_partials, st, launches); });
 }
 
 cudaError_t launch_finalize(const LaunchInfo &li, int k, const uint32_t *d_table, uint8_t *d_flags, const fkb_partials *d_partials,

@@ -11,6 +11,7 @@ enum CountVariant : int {
     VARIANT_AUTO = 0,
     VARIANT_DIRECT = 1,   // fused encode + one red.global per window into the L2-resident table
     VARIANT_BUCKET = 2,   // W-mers at stride S routed through shared memory to per-bucket smem counters, then folded
+    VARIANT_SMEM = 3,     // k <= 8: single pass, the whole 4^k table privatised per CTA in shared memory (fkb_smallk.cu)
 };
 
 // device scratch of VARIANT_BUCKET (owned by the context)
@@ -44,6 +45,11 @@ bool bucket_folds_in_shared(int k);  // core buckets (k >= 9): pass 2 folds in s
 int bucket_segments_per_sm();  // pass-1 CTAs per SM (each owns one segment per bucket)
 cudaError_t launch_count_bucketed(const LaunchInfo &li, const BucketScratch &bs, const uint8_t *d_stream, uint64_t lo, uint64_t hi, int k,
                                   uint32_t *d_table, uint8_t *d_flags, fkb_partials *d_partials, cudaStream_t st, int *launches);
+
+// single-pass shared-memory path for k <= 8 (fkb_smallk.cu)
+uint64_t smallk_unit_bytes(int k);   // interior granularity (one warp iteration), 0 when k > 8
+cudaError_t launch_count_smallk(const LaunchInfo &li, const uint8_t *d_stream, uint64_t lo, uint64_t hi, int k, uint32_t *d_table, uint8_t *d_flags,
+                                fkb_partials *d_partials, cudaStream_t st, int *launches);
 
 cudaError_t launch_count(const LaunchInfo &li, const uint8_t *d_stream, uint64_t begin, uint64_t end, int k,
                          uint32_t *d_table, uint8_t *d_flags, fkb_partials *d_partials, cudaStream_t st,

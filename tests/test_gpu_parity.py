@@ -241,6 +241,64 @@ def test_bucketed_variant_skewed_composition_uses_the_back_region(bucketed, harn
     assert_counts_equal(got, harness.oracle_count_stream(s, k))
 
 
+# ---- k <= 8: the single-pass shared-memory path (fkb_smallk.cu) ------------------------------------------------
+@pytest.fixture()
+def smem_path(counter):
+    counter.set_variant(3)
+    yield counter
+    counter.set_variant(0)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_smem_variant_matches_oracle(smem_path, harness, k):
+    """config-5 shape (N runs + soft-masked runs: the general path with its per-run events), whole and as three unaligned
+    pieces; then clean sequence (the predicate-free path) and 1001-base records (a reset every kilobyte)"""
+    from findkmer_b200 import synth
+    stream = smem_path.strip(synth.render(synth.config5(n_bases=1_500_000)))
+    want = harness.oracle_count_stream(stream, k)
+    got, _ = _device_count(smem_path, stream, k)
+    assert_counts_equal(got, want)
+    got, _ = _device_count(smem_path, stream, k, 12345, len(stream) - 777, pieces=3)
+    sub = harness.oracle_count_stream(stream[:len(stream) - 777], k)
+    head = harness.oracle_count_stream(stream[:12345], k)
+    assert np.array_equal(got.table, sub.table - head.table)
+    for lay in (synth.config2(n_bases=1_200_000), synth.config3(n_records=1500)):
+        stream = smem_path.strip(synth.render(lay))
+        got, _ = _device_count(smem_path, stream, k)
+        assert_counts_equal(got, harness.oracle_count_stream(stream, k))
+
+
+@pytest.mark.parametrize("k", [6, 8])
+def test_smem_variant_junk_and_hot_counters(smem_path, harness, k):
+    """junk bytes of every kind (unknown-character count included), and poly-A with sparse substitutions: one counter takes
+    almost everything, so the 16-bit counters of k = 8 drain at 0x8000 many times; both must stay exact"""
+    for seed in range(3):
+        data = random_fasta(seed, 300_000)
+        stream = smem_path.strip(data)
+        got, _ = _device_count(smem_path, stream, k)
+        assert_counts_equal(got, harness.oracle_count_stream(stream, k))
+    rng = np.random.default_rng(3)
+    s = np.full(6_000_000, ord("A"), dtype=np.uint8)
+    idx = rng.integers(0, s.size, size=4000)
+    s[idx] = np.frombuffer(b"CGTN", dtype=np.uint8)[rng.integers(0, 4, size=idx.size)]
+    got, _ = _device_count(smem_path, s, k)
+    want = harness.oracle_count_stream(s, k)
+    assert int(want.table.max()) > 1_000_000
+    assert_counts_equal(got, want)
+
+
+def test_auto_takes_the_smem_path_for_small_k(counter, harness):
+    """variant 0 (what users get): k <= 8 on a few megabases runs count_smem_kernel, not the bucketed kernels
+    (3 launches: the kernel, the edge slivers, ... plus finalize)"""
+    from findkmer_b200 import synth
+    stream = counter.strip(synth.render(synth.config5(n_bases=3_000_000)))
+    for k in (6, 8):
+        n0 = counter.launches
+        got, _ = _device_count(counter, stream, k)
+        assert 3 <= counter.launches - n0 <= 6
+        assert_counts_equal(got, harness.oracle_count_stream(stream, k))
+
+
 def test_phase_times_of_the_bucketed_path(bucketed):
     """option phase_events: the library records CUDA events around pass 1 / pass 2 / fold; results unchanged"""
     import ctypes
