@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--ref-sample-bases", type=int, default=4_000_000, help="per-step sample of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the config-5 (k = 8, dirty input) measurement")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3  # timing rule: at least 3 warm-up steps
@@ -284,11 +285,40 @@ def main():
             dist.all_reduce(t3, op=dist.ReduceOp.MAX)
             phase_ms = [float(x) for x in t3]
 
-    # sanity of what was timed (rank 0): conservation over the record layout
+    # ---- parity of what was timed (outside the timed region) ----
+    # (1) conservation over the record layout; (2) at the metric's own size, the table and scalars against the oracle's full-size
+    # record (tests/golden/golden_fullsize.json: sha256 of the table of a record-parallel run of oracle/kmer_oracle.c);
+    # (3) N > 1: rank 0 counts the WHOLE stream alone and the NCCL-reduced table, the flag-derived node count and every scalar
+    # must be bit-identical to that single-GPU result.
+    parity = {}
+    expect = sum(max(0, raw_lay.record_bases(r) - k + 1) for r in range(raw_lay.n_records))
     if rank == 0:
+        import hashlib
         c = FkbCounts.from_buffer_copy(d_counts.cpu().numpy().tobytes())
-        expect = sum(max(0, raw_lay.record_bases(r) - k + 1) for r in range(raw_lay.n_records))
         assert c.n_kmers == expect and c.base_total == args.bases and not c.rollover, (c.n_kmers, expect, c.base_total)
+        reduced_table = acc.table.clone()
+        parity["conservation"] = "ok"
+        gpath = ROOT / "tests" / "golden" / "golden_fullsize.json"
+        if gpath.exists() and args.bases == N_BASES:
+            g = json.loads(gpath.read_text())["records"].get(f"config4_k{k}")
+            if g:
+                sha = hashlib.sha256(reduced_table.cpu().numpy().astype("<u4").tobytes()).hexdigest()
+                assert sha == g["table_sha256"], "count table differs from the oracle's full-size record"
+                assert (c.n_kmers, c.base_total, list(c.base_count), c.node_count, c.unknown_chars) == \
+                       (g["n_kmers"], g["base_total"], g["base_count"], g["node_count"], g["unknown_chars"])
+                parity["oracle_fullsize"] = "ok: sha256(table) + 8 scalars == tests/golden/golden_fullsize.json config4_k%d" % k
+        if world > 1:
+            whole = counter.synth_fasta_device(str_lay)
+            acc1 = counter.new_accumulators(k)
+            counter.count_stream_device(whole, k, acc1)
+            one = counter.finalize_device(acc1, stream_total, fetch_table=False)
+            assert torch.equal(acc1.table, reduced_table), "NCCL-reduced table differs from the single-GPU table"
+            assert (one.n_kmers, one.base_total, tuple(one.base_count), one.node_count, one.unknown_chars, one.runs_ge_k, one.valid_bases) == \
+                   (c.n_kmers, c.base_total, tuple(c.base_count), c.node_count, c.unknown_chars, c.runs_ge_k, c.valid_bases)
+            parity["parity_n"] = f"ok: {world}-rank reduced table, node count and scalars bit-identical to one GPU counting the whole stream"
+            del whole, acc1
+            torch.cuda.empty_cache()
+        del reduced_table
 
     # ---- roofline of the dominant kernel (count): algorithmic bytes = 1 B/base of stream + the 4^k x 4 B table ----
     peaks_path = ROOT / "MEASURED_PEAKS.json"
@@ -383,6 +413,49 @@ def main():
                "path": "raw FASTA bytes in pinned host memory -> H2D in 128 MiB chunks -> device strip (record/line compaction) -> "
                        "count -> [reduce] -> finalize -> table + counts D2H; pageable inputs use the host loader threads instead"}
 
+    # ---- secondary workload (rank 0, N = 1): BASELINE.json config 5 -- 3.1 Gbp with N runs and soft-masked lower case, k = 8 ----
+    secondary = None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        import hashlib
+        k2 = 8
+        lay5 = synth.config5(n_bases=args.bases).stripped()
+        d5 = counter.synth_fasta_device(lay5)
+        acc5 = counter.new_accumulators(k2)
+        d_counts5 = torch.zeros(12, dtype=torch.int64, device=dev)
+        ev5 = []
+        for i in range(3 + 5):
+            counter._check(lib.fkb_zero_device(ctx, k2, acc5.table.data_ptr(), acc5.flags.data_ptr(), acc5.partials.data_ptr(), st.cuda_stream))
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record(st)
+            counter.count_stream_device(d5, k2, acc5)
+            e1.record(st)
+            counter._check(lib.fkb_finalize_device(ctx, k2, acc5.table.data_ptr(), acc5.flags.data_ptr(), acc5.partials.data_ptr(),
+                                                   d5.numel(), d_counts5.data_ptr(), st.cuda_stream))
+            e2.record(st)
+            if i >= 3:
+                ev5.append((e0, e1, e2))
+        torch.cuda.synchronize()
+        ms5 = sum(a.elapsed_time(c_) for a, _, c_ in ev5) / len(ev5)
+        kms5 = sum(a.elapsed_time(b_) for a, b_, _ in ev5) / len(ev5)
+        c5 = FkbCounts.from_buffer_copy(d_counts5.cpu().numpy().tobytes())
+        par5 = "unchecked (no golden record for this size)"
+        gpath = ROOT / "tests" / "golden" / "golden_fullsize.json"
+        if gpath.exists() and args.bases == N_BASES:
+            g = json.loads(gpath.read_text())["records"]["config5_k8"]
+            sha = hashlib.sha256(acc5.table.cpu().numpy().astype("<u4").tobytes()).hexdigest()
+            assert sha == g["table_sha256"] and (c5.n_kmers, c5.base_total, list(c5.base_count), c5.node_count, c5.unknown_chars) == \
+                (g["n_kmers"], g["base_total"], g["base_count"], g["node_count"], g["unknown_chars"])
+            par5 = "ok: sha256(table) + scalars == tests/golden/golden_fullsize.json config5_k8"
+        bytes5 = d5.numel() + (4 ** k2) * 4
+        secondary = {"config": f"config 5: synthetic {args.bases / 1e9:.3g} Gbp, 24 records, ~5 % of positions in N runs + ~10 % soft-masked lower case, k={k2}",
+                     "value": args.bases / (ms5 * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms5, "steps": len(ev5),
+                     "kernel": "count_smem_kernel<8> (single pass, 65536 16-bit counters per CTA in shared memory) + edge slivers",
+                     "roofline": {"bound": "hbm", "achieved": bytes5 / (kms5 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                  "frac": bytes5 / (kms5 * 1e-3) / 1e9 / peak, "kernel_ms": kms5, "algorithmic_bytes_per_launch": bytes5},
+                     "parity": par5}
+        del d5, acc5
+        torch.cuda.empty_cache()
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         with tempfile.TemporaryDirectory() as d:
@@ -395,7 +468,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
                 "data": "synthetic", "config": workload_config(args), "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_info}
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_info, "parity": parity, "secondary": secondary}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

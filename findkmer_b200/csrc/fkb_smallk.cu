@@ -22,23 +22,25 @@ namespace fkb {
 
 namespace {
 
-constexpr int kG = 2;                 // 16-byte groups per lane per iteration
-constexpr int kCH = 16 * kG;          // bytes per lane per iteration
-constexpr uint64_t kWSpan = 32ull * kCH;  // bytes per warp iteration
+constexpr uint64_t kUnit = 1024;      // interior granularity: a whole number of warp iterations for every G below
 constexpr uint32_t kEvTile = 2048;    // warp iterations between two flushes of the 32-bit event counters
 
 template <int K> struct SmCfg {
     static constexpr bool kPacked = (K == 8);                     // 16-bit counters, two per word, drained at 0x8000
-    static constexpr int kThreads = kPacked ? 1024 : 512;
+#ifndef FKB_SK8_THREADS
+#define FKB_SK8_THREADS 1024
+#endif
+    static constexpr int kThreads = kPacked ? FKB_SK8_THREADS : 512;
     static constexpr int kMinBlocks = kPacked ? 1 : 2;
     static constexpr uint32_t kTableBytes = kPacked ? (2u << (2 * K)) : (4u << (2 * K));
+    // 16-byte groups per lane per iteration.  Measured on B200 (profiles/r02_sweep_smallk.txt): k = 8 is faster with one group
+    // (config 4 1.44 -> 1.42 ms, config 5 4.21 -> 3.86 ms: the packed path keeps 8 old values per batch live), k <= 7 with two
+    static constexpr int kGroups = kPacked ? 1 : 2;
 };
 
-// predicated shared-memory reduction (no return value: ptxas keeps the predicate instead of branching)
-__device__ __forceinline__ void reds_inc_if(uint32_t saddr, uint32_t pred)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], 1;\n\t}" ::"r"(saddr), "r"(pred) : "memory");
-}
+// shared-memory reductions (no return value).  ptxas turns a PREDICATED shared atomic into a branch around it (BSSY / BRA /
+// ATOMS / BSYNC per item), so the general path adds 0 instead of skipping.
+__device__ __forceinline__ void reds_add(uint32_t saddr, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
 __device__ __forceinline__ void reds_inc(uint32_t saddr) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(saddr) : "memory"); }
 __device__ __forceinline__ uint32_t atoms_add(uint32_t saddr, uint32_t v)
 {
@@ -68,12 +70,15 @@ count_smem_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers,
 {
     constexpr int kThreads = SmCfg<K>::kThreads, kWarps = kThreads / 32;
     constexpr bool PACKED = SmCfg<K>::kPacked;
+    constexpr int kG = SmCfg<K>::kGroups, kCH = 16 * kG;      // bytes per lane per iteration
+    constexpr uint64_t kWSpan = 32ull * kCH;                   // bytes per warp iteration
     constexpr uint32_t MASK = (1u << (2 * K)) - 1u;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t *cnt = reinterpret_cast<uint32_t *>(smem_raw);
     __shared__ uint32_t ev[16];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t cnt_sa = (uint32_t)__cvta_generic_to_shared(cnt);
+    const uint32_t junk_sa = cnt_sa + SmCfg<K>::kTableBytes + 4u * (uint32_t)lane;  // one junk word per lane (one bank each), behind the table
 
     for (uint32_t i = threadIdx.x; i < SmCfg<K>::kTableBytes / 16; i += kThreads) reinterpret_cast<uint4 *>(cnt)[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x < 16) ev[threadIdx.x] = 0;
@@ -90,24 +95,31 @@ count_smem_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers,
     uint32_t t_unknown = 0, t_dummy = 0, n_fast = 0;
     unsigned long long t_windows = 0, t_valid = 0;
 
-    // software pipeline: `r0` = raw bytes of iteration it, `r1` = of it + 1 (in flight)
-    uint4 r0[kG], r1[kG];
+    // `r0` = raw bytes of the iteration about to be processed; the loads of iteration it + 1 are issued as soon as iteration
+    // it's bytes have been encoded (a whole iteration -- several thousand cycles -- before they are needed; no second buffer:
+    // its registers were spilled at 1024 threads x 64 registers)
+    uint4 r0[kG];
     Group carry = pack_group(ldg128(lane_base - (uint64_t)lane * kCH - 16), t_dummy);  // the 16 bytes in front of the region (same address for all lanes)
 #pragma unroll
     for (int g = 0; g < kG; ++g) r0[g] = ldg128_if(lane_base + 16 * g, my_iters > 0);
-#pragma unroll
-    for (int g = 0; g < kG; ++g) r1[g] = ldg128_if(lane_base + kWSpan + 16 * g, my_iters > 1);
 
     for (uint32_t tile0 = 0; tile0 < max_iters; tile0 += kEvTile) {
         const uint32_t tile_end = min(tile0 + kEvTile, my_iters);
         for (uint32_t it = tile0; it < tile_end; ++it) {
             Group grp[kG + 1];  // grp[0] = the 16 bytes in front of my chunk, grp[1..G] = my chunk
+            {
+                // fast encode: codes only, validity accumulated over the lane's 16*G bytes and tested once; exact per-byte masks
+                // (and the unknown-character count) only for a lane that holds a byte that is not a base
+                ValidAcc va;
 #pragma unroll
-            for (int g = 0; g < kG; ++g) grp[g + 1] = pack_group(r0[g], t_unknown);
+                for (int g = 0; g < kG; ++g) {
+                    grp[g + 1].code = pack_codes_fast(r0[g], va);
+                    grp[g + 1].valid = 0xFFFFu;
+                }
+                if (va.bad()) {
 #pragma unroll
-            for (int g = 0; g < kG; ++g) {
-                r0[g] = r1[g];
-                r1[g] = ldg128_if(lane_base + (uint64_t)(it + 2) * kWSpan + 16 * g, it + 2 < my_iters);
+                    for (int g = 0; g < kG; ++g) grp[g + 1] = pack_group(r0[g], t_unknown);
+                }
             }
             const uint32_t up_c = __shfl_sync(0xffffffffu, grp[kG].code, (lane + 31) & 31);
             const uint32_t up_v = __shfl_sync(0xffffffffu, grp[kG].valid, (lane + 31) & 31);
@@ -142,6 +154,10 @@ count_smem_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers,
                 }
             }
 
+            // next iteration's bytes: issued HERE, behind the event handler -- a call waits for every load in flight
+#pragma unroll
+            for (int g = 0; g < kG; ++g) r0[g] = ldg128_if(lane_base + (uint64_t)(it + 1) * kWSpan + 16 * g, it + 1 < my_iters);
+
             // the 16 windows of every group: one shared-memory atomic each, 8 back to back.  CLEAN (warp-uniform): every window
             // exists, no predicates at all.
             auto count_groups = [&](auto clean_t) {
@@ -154,30 +170,35 @@ count_smem_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers,
 #pragma unroll
                             for (int i = 8 * h; i < 8 * h + 8; ++i) {
                                 const uint32_t f = (i == 15) ? grp[g].code : __funnelshift_r(grp[g].code, grp[g - 1].code, 2 * (15 - i));
-                                const uint32_t sa = mad_u32(f & MASK, 4u, cnt_sa);
-                                if constexpr (CLEAN) reds_inc(sa);
-                                else reds_inc_if(sa, emit[g] & (1u << (15 - i)));
+                                uint32_t sa = mad_u32(f & MASK, 4u, cnt_sa);
+                                // no window here: the increment goes to this lane's junk word (a predicated shared atomic would become a
+                                // branch per item; adding 0 in place would pile the identical garbage windows of an N run onto one address)
+                                if constexpr (!CLEAN) sa = (emit[g] & (1u << (15 - i))) ? sa : junk_sa;
+                                reds_inc(sa);
                             }
                         } else {
-                            uint32_t f[8], old[8], top[8], any = 0;
+                            uint32_t f[8], old[8], any = 0;
 #pragma unroll
                             for (int i = 8 * h; i < 8 * h + 8; ++i) {
                                 const int j = i - 8 * h;
                                 f[j] = (i == 15) ? grp[g].code : __funnelshift_r(grp[g].code, grp[g - 1].code, 2 * (15 - i));
-                                const uint32_t sa = mad_u32(f[j] & 0xFFFEu, 2u, cnt_sa);        // word of counters 2n, 2n+1
+                                uint32_t sa = mad_u32(f[j] & 0xFFFEu, 2u, cnt_sa);              // word of counters 2n, 2n+1
                                 uint32_t inc = mad_u32(f[j] & 1u, 0xFFFFu, 1u);                 // odd k-mer: the high half
-                                if constexpr (!CLEAN) inc = (emit[g] & (1u << (15 - i))) ? inc : 0u;  // no window here: add nothing
-                                top[j] = inc << 15;                                             // bit 15 of the half this item increments
+                                if constexpr (!CLEAN) {                                         // no window here: add nothing, to the junk word
+                                    const bool e = (emit[g] & (1u << (15 - i))) != 0;
+                                    sa = e ? sa : junk_sa;
+                                    inc = e ? inc : 0u;  // (so the junk words stay 0 and can never look like a counter at 0x8000 below)
+                                }
                                 old[j] = atoms_add(sa, inc);
                             }
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) any |= old[j] & top[j];
-                            if (any) {
+                            for (int j = 0; j < 8; ++j) any |= old[j];
+                            if (any & 0x80008000u) {  // some touched word has a half at or above 0x8000 (this item's or its neighbour's): look closer
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) {
                                     const uint32_t x = f[j] & MASK;
                                     const uint32_t half = (x & 1u) ? (old[j] >> 16) : (old[j] & 0xFFFFu);
-                                    if (top[j] && half == 0x8000u) drain_packed(cnt_sa + (x & 0xFFFEu) * 2u, x & 1u, x, table_k);
+                                    if (half == 0x8000u) drain_packed(cnt_sa + (x & 0xFFFEu) * 2u, x & 1u, x, table_k);
                                 }
                             }
                         }
@@ -233,26 +254,27 @@ cudaError_t run_smallk(const LaunchInfo &li, const uint8_t *d_stream, uint64_t l
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     const uint64_t dev_bit = 1ull << (dev & 63);
-    if (SmCfg<K>::kTableBytes > 48 * 1024 && !(attr_done.load(std::memory_order_acquire) & dev_bit)) {
-        e = cudaFuncSetAttribute(count_smem_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmCfg<K>::kTableBytes);
+    if (SmCfg<K>::kTableBytes + 128 > 48 * 1024 && !(attr_done.load(std::memory_order_acquire) & dev_bit)) {
+        e = cudaFuncSetAttribute(count_smem_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmCfg<K>::kTableBytes + 128);
         if (e != cudaSuccess) return e;
         attr_done.fetch_or(dev_bit, std::memory_order_release);
     }
+    constexpr uint64_t kWSpan = 32ull * 16 * SmCfg<K>::kGroups;
     const uint64_t n_witers = (hi - lo) / kWSpan;
     constexpr int kWarps = SmCfg<K>::kThreads / 32;
     if ((n_witers / kWarps) >> 32) return cudaErrorInvalidValue;
-    // every CTA pays 4^k reds at the end: use fewer CTAs on short ranges (>= 16 warp iterations = 16 KiB per warp)
+    // every CTA pays 4^k reds at the end: use fewer CTAs on short ranges (>= 16 KiB per warp)
     uint64_t ctas = (uint64_t)li.sm_count * SmCfg<K>::kMinBlocks;
-    const uint64_t want = (n_witers + 16ull * kWarps - 1) / (16ull * kWarps);
+    const uint64_t want = ((hi - lo) / 1024 + 16ull * kWarps - 1) / (16ull * kWarps);
     if (want < ctas) ctas = want ? want : 1;
-    count_smem_kernel<K><<<(unsigned)ctas, SmCfg<K>::kThreads, SmCfg<K>::kTableBytes, st>>>(d_stream, lo, n_witers, d_table, d_flags, d_partials);
+    count_smem_kernel<K><<<(unsigned)ctas, SmCfg<K>::kThreads, SmCfg<K>::kTableBytes + 128, st>>>(d_stream, lo, n_witers, d_table, d_flags, d_partials);
     if (launches) ++*launches;
     return cudaGetLastError();
 }
 
 }  // namespace
 
-uint64_t smallk_unit_bytes(int k) { return (k >= 1 && k <= 8) ? kWSpan : 0; }
+uint64_t smallk_unit_bytes(int k) { return (k >= 1 && k <= 8) ? kUnit : 0; }
 
 cudaError_t launch_count_smallk(const LaunchInfo &li, const uint8_t *d_stream, uint64_t lo, uint64_t hi, int k, uint32_t *d_table, uint8_t *d_flags,
                                 fkb_partials *d_partials, cudaStream_t st, int *launches)
