@@ -30,7 +30,7 @@ EXPORTS = [
     "fkb_strip_fasta", "fkb_alloc_pinned", "fkb_free_pinned",
     "fkb_table_entries", "fkb_prefix_flags_bytes", "fkb_zero_device", "fkb_count_stream_device", "fkb_finalize_device",
     "fkb_count_fasta_host", "fkb_count_stream_host", "fkb_count_fasta_host_range", "fkb_count_file",
-    "fkb_count_fasta_host_multi", "fkb_count_file_multi",
+    "fkb_count_fasta_host_multi", "fkb_count_file_multi", "fkb_count_fasta_host_gpus", "fkb_count_file_gpus", "fkb_device_count",
     "fkb_write_base_stats", "fkb_write_histogram", "fkb_write_histogram_tsv", "fkb_max_nodes",
     "fkb_synth_fasta_device", "fkb_launch_count",
 ]
@@ -121,6 +121,12 @@ def load() -> ctypes.CDLL:
     lib.fkb_count_fasta_host_multi.restype = c_int
     lib.fkb_count_file_multi.argtypes = [ctx, c_char_p, POINTER(c_int), c_int, POINTER(c_void_p), POINTER(FkbCounts)]
     lib.fkb_count_file_multi.restype = c_int
+    lib.fkb_count_fasta_host_gpus.argtypes = [POINTER(c_int), c_int, c_void_p, c_size_t, c_int, c_void_p, POINTER(FkbCounts), c_char_p, c_size_t]
+    lib.fkb_count_fasta_host_gpus.restype = c_int
+    lib.fkb_count_file_gpus.argtypes = [POINTER(c_int), c_int, c_char_p, c_int, c_void_p, POINTER(FkbCounts), c_char_p, c_size_t]
+    lib.fkb_count_file_gpus.restype = c_int
+    lib.fkb_device_count.argtypes = []
+    lib.fkb_device_count.restype = c_int
     lib.fkb_count_file.argtypes = [ctx, c_char_p, c_int, c_void_p, POINTER(FkbCounts)]
     lib.fkb_count_file.restype = c_int
     lib.fkb_write_base_stats.argtypes = [c_void_p, c_void_p, c_int, POINTER(FkbCounts), POINTER(ctypes.c_longdouble * 4)]

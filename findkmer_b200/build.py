@@ -29,7 +29,7 @@ NVCC_FLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-
 # the writer must not be compiled with fast-math or FMA contraction: its output is compared byte for byte
 CXX_FLAGS = ["-O2", "-fPIC", "-std=c++17", "-Wall", "-Wextra", "-ffp-contract=off", "-I", str(ROOT / "include"), "-I", str(CSRC)]
 
-CU_SOURCES = ["fkb_kernels.cu", "fkb_bucket.cu", "fkb_smallk.cu", "fkb_strip.cu", "fkb_api.cu"]
+CU_SOURCES = ["fkb_kernels.cu", "fkb_bucket.cu", "fkb_bucket2.cu", "fkb_smallk.cu", "fkb_strip.cu", "fkb_api.cu"]
 CXX_SOURCES = ["fkb_loader.cpp", "fkb_writer.cpp"]
 
 
@@ -67,7 +67,7 @@ def build(verbose: bool = False, force: bool = False) -> Path:
     exe = BIN / "findKmer"
     if main_src.exists() and (force or _stale(exe, [main_src, LIB] + headers)):
         _run(["g++"] + CXX_FLAGS + [main_src, "-o", exe, "-L", PKG, "-lfindkmer_b200", "-Wl,-rpath,$ORIGIN/..", "-lpthread"], verbose)
-    for name in ("fkb_ubench", "fkb_ubench_bulk"):
+    for name in ("fkb_ubench", "fkb_ubench_bulk", "fkb_ubench_stage"):
         ub_src = CSRC / (name + ".cu")
         ub = BIN / name
         if ub_src.exists() and (force or _stale(ub, [ub_src] + headers)):

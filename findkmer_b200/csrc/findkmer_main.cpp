@@ -310,15 +310,24 @@ int main(int argc, char **argv)
     fflush(stdout);
 
     // ---- the counting path: findKmer() -> GPU ----
+    std::vector<int> ks = cfg.sweep.empty() ? std::vector<int>{cfg.k} : cfg.sweep;
+    // -g N (extension): contiguous shards of the file on the first N GPUs of this box, tables summed on GPU 0 over NVLink
+    const int n_gpus = cfg.gpus > 1 ? (cfg.gpus < fkb_device_count() ? cfg.gpus : fkb_device_count()) : 1;
+    if (cfg.gpus > 1 && n_gpus < cfg.gpus)
+        fprintf(stderr, "findKmer (B200 engine): -g %d asked for, %d GPU(s) present: using %d\n", cfg.gpus, fkb_device_count(), n_gpus > 0 ? n_gpus : 1);
+    const bool multi_gpu = n_gpus > 1 && ks.size() == 1;
+    if (n_gpus > 1 && !multi_gpu) fprintf(stderr, "findKmer (B200 engine): -K sweeps run on one GPU; -g ignored\n");
     fkb_context *ctx = nullptr;
-    int status = fkb_create(0, &ctx);
-    if (status != FKB_OK) {
-        fprintf(stderr, "findKmer (B200 engine): no usable sm_100 GPU (%s); this build has no CPU fallback\n", fkb_status_string(status));
-        fclose(csv);
-        return EXIT_FAILURE;
+    int status = FKB_OK;
+    if (!multi_gpu) {
+        status = fkb_create(0, &ctx);
+        if (status != FKB_OK) {
+            fprintf(stderr, "findKmer (B200 engine): no usable sm_100 GPU (%s); this build has no CPU fallback\n", fkb_status_string(status));
+            fclose(csv);
+            return EXIT_FAILURE;
+        }
     }
     phase_mark("fkb_create (CUDA context)");
-    std::vector<int> ks = cfg.sweep.empty() ? std::vector<int>{cfg.k} : cfg.sweep;
     std::vector<std::vector<uint32_t>> tables(ks.size());
     std::vector<uint32_t *> table_ptrs(ks.size());
     std::vector<fkb_counts> all_counts(ks.size());
@@ -332,7 +341,12 @@ int main(int argc, char **argv)
         return EXIT_FAILURE;
     }
     memset(all_counts.data(), 0, sizeof(fkb_counts) * ks.size());
-    if (ks.size() == 1) status = fkb_count_file(ctx, cfg.sequence_file.c_str(), ks[0], table_ptrs[0], &all_counts[0]);
+    char gpus_err[512] = "";
+    if (multi_gpu) {
+        std::vector<int> devices(n_gpus);
+        for (int i = 0; i < n_gpus; ++i) devices[i] = i;
+        status = fkb_count_file_gpus(devices.data(), n_gpus, cfg.sequence_file.c_str(), ks[0], table_ptrs[0], &all_counts[0], gpus_err, sizeof gpus_err);
+    } else if (ks.size() == 1) status = fkb_count_file(ctx, cfg.sequence_file.c_str(), ks[0], table_ptrs[0], &all_counts[0]);
     else status = fkb_count_file_multi(ctx, cfg.sequence_file.c_str(), ks.data(), (int)ks.size(), table_ptrs.data(), all_counts.data());
     phase_mark("count (mmap, load, GPU)");
     if (status == FKB_ERR_EMPTY_INPUT) {
@@ -350,7 +364,7 @@ int main(int argc, char **argv)
         return EXIT_FAILURE;
     }
     if (status != FKB_OK) {
-        fprintf(stderr, "findKmer (B200 engine): %s\n", fkb_last_error(ctx));
+        fprintf(stderr, "findKmer (B200 engine): %s\n", ctx ? fkb_last_error(ctx) : gpus_err);
         fclose(csv);
         fkb_destroy(ctx);
         return EXIT_FAILURE;
@@ -360,7 +374,7 @@ int main(int argc, char **argv)
     struct Teardown {
         std::thread t;
         ~Teardown() { if (t.joinable()) t.join(); }
-    } teardown{std::thread([ctx] { fkb_destroy(ctx); })};
+    } teardown{std::thread([ctx] { if (ctx) fkb_destroy(ctx); })};
     if (all_counts[0].unknown_chars)
         fprintf(stderr, "Unknown character processed! File may be corrupted. (%llu such characters; the reference prints one line each)\n",
                 (unsigned long long)all_counts[0].unknown_chars);

@@ -120,7 +120,7 @@ int ensure_bucket_scratch(fkb_context *ctx, int k, uint64_t range_bytes)
     const int S = fkb::bucket_stride_for(k);
     if (!S || ctx->forced_variant == fkb::VARIANT_DIRECT || ctx->forced_variant == fkb::VARIANT_SMEM) return FKB_OK;
     if (k <= 8 && ctx->forced_variant != fkb::VARIANT_BUCKET) return FKB_OK;  // k <= 8 takes the single-pass shared-memory path (fkb_smallk.cu)
-    if (range_bytes < fkb::bucket_min_bytes(k) && ctx->forced_variant != fkb::VARIANT_BUCKET) return FKB_OK;  // the direct kernel will run
+    if (range_bytes < fkb::bucket_min_bytes(k) && ctx->forced_variant != fkb::VARIANT_BUCKET && ctx->forced_variant != fkb::VARIANT_BUCKET16) return FKB_OK;  // the direct kernel will run
     const uint64_t items = range_bytes / S + 1;
     const uint64_t nb = (uint64_t)fkb::bucket_count(), n_cta = (uint64_t)ctx->sm_count;
     const uint64_t n_seg = n_cta * (uint64_t)fkb::bucket_segments_per_sm();
@@ -600,7 +600,7 @@ int fkb_device_info(fkb_context *ctx, int *sm_count, int *cc_major, int *cc_mino
 int fkb_set_option(fkb_context *ctx, const char *name, long value)
 {
     if (!ctx || !name) return FKB_ERR_BAD_ARG;
-    if (!strcmp(name, "variant") && value >= 0 && value <= 3) {
+    if (!strcmp(name, "variant") && value >= 0 && value <= 4) {
         ctx->forced_variant = (int)value;
         return FKB_OK;
     }
@@ -922,6 +922,142 @@ int fkb_count_file(fkb_context *ctx, const char *path, int k, uint32_t *table, f
     int s = fkb_count_fasta_host(ctx, (const uint8_t *)map, (size_t)st.st_size, k, table, counts);
     munmap(map, (size_t)st.st_size);
     return s;
+}
+
+// ---- several GPUs of one box behind the C boundary ------------------------------------------------
+// The reference's only parallelism is one OS process per k (k6thru11fullANDupstream.sh:16-24).  Here ONE scan is sharded:
+// the file image is cut into n contiguous byte ranges, one host thread + one context per GPU counts its range (a window
+// belongs to the shard that owns its LAST byte; the 16-byte left halo comes from the look-back context), and the exchange
+// step is one pass on devices[0] that adds every other GPU's table / flags / partials -- read directly from peer memory over
+// NVLink when the devices can map each other, through a staging copy otherwise -- before finalize.
+int fkb_count_fasta_host_gpus(const int *devices, int n_devices, const uint8_t *fasta, size_t len, int k, uint32_t *table, fkb_counts *counts,
+                              char *err, size_t err_len)
+{
+    auto say = [&](const char *msg) { if (err && err_len) snprintf(err, err_len, "%s", msg); };
+    if (!devices || n_devices < 1 || n_devices > 64 || !table || !counts || (len && !fasta)) return FKB_ERR_BAD_ARG;
+    if (k < 1 || k > FKB_MAX_K) { say("not a valid value for k"); return FKB_ERR_BAD_K; }
+    if (len == 0) { say("Sequence File Is Empty"); return FKB_ERR_EMPTY_INPUT; }
+    const int n = n_devices;
+    std::vector<fkb_context *> ctx(n, nullptr);
+    struct Shard { size_t a = 0, b = 0; uint64_t stream_bytes = 0, stop = UINT64_MAX; int ends_in_header = 0; int status = FKB_OK; };
+    std::vector<Shard> sh(n);
+    for (int i = 0; i < n; ++i) {  // raw byte ranges; any cut is exact (the shard derives its halo and header state from the look-back)
+        sh[i].a = (size_t)((unsigned __int128)len * i / n);
+        sh[i].b = (size_t)((unsigned __int128)len * (i + 1) / n);
+    }
+    auto cleanup = [&] { for (auto *c : ctx) if (c) fkb_destroy(c); };
+    {
+        std::vector<std::thread> pool;
+        for (int i = 0; i < n; ++i)
+            pool.emplace_back([&, i] {
+                Shard &s = sh[i];
+                s.status = fkb_create(devices[i], &ctx[i]);
+                if (s.status != FKB_OK) return;
+                fkb_context *c = ctx[i];
+                if ((s.status = ensure_table(c, k)) != FKB_OK) return;
+                if ((s.status = fkb_zero_device(c, k, c->d_table, c->d_flags, c->d_partials, c->s_pipe)) != FKB_OK) return;
+                if (s.b > s.a)
+                    s.status = fkb_count_fasta_host_range(c, fasta, s.b, s.a, k, c->d_table, c->d_flags, c->d_partials, &s.stream_bytes, &s.stop, &s.ends_in_header);
+                cudaStreamSynchronize(c->s_pipe);
+            });
+        for (auto &t : pool) t.join();
+    }
+    for (int i = 0; i < n; ++i)
+        if (sh[i].status != FKB_OK) {
+            say(ctx[i] ? fkb_last_error(ctx[i]) : "fkb_create failed: no usable sm_100 GPU for a shard (no CPU fallback exists)");
+            const int st = sh[i].status;
+            cleanup();
+            return st;
+        }
+    // a byte 0xFF outside a header ends the reference's scan (:975,:988): shards that begin behind the first one count nothing
+    uint64_t stop = UINT64_MAX;
+    for (int i = 0; i < n; ++i) stop = sh[i].stop < stop ? sh[i].stop : stop;
+    int last_live = n - 1;
+    if (stop != UINT64_MAX)
+        for (int i = 0; i < n; ++i)
+            if (sh[i].a <= stop && stop < sh[i].b) last_live = i;
+    if (stop == UINT64_MAX) {
+        int tail = n - 1;
+        while (tail > 0 && sh[tail].b == sh[tail].a) --tail;
+        if (sh[tail].ends_in_header) {
+            say(fkb_status_string(FKB_ERR_UNTERMINATED_HEADER));
+            cleanup();
+            return FKB_ERR_UNTERMINATED_HEADER;
+        }
+    }
+    fkb_context *c0 = ctx[0];
+    int status = FKB_OK;
+    uint64_t stream_bytes = sh[0].stream_bytes;
+    cudaSetDevice(c0->device);
+    uint32_t *tmp_table = nullptr;
+    uint8_t *tmp_flags = nullptr;
+    fkb_partials *tmp_partials = nullptr;
+    for (int i = 1; i <= last_live && status == FKB_OK; ++i) {
+        fkb_context *ci = ctx[i];
+        stream_bytes += sh[i].stream_bytes;
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, c0->device, ci->device);
+        if (can) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(ci->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+            if (e != cudaSuccess) { cudaGetLastError(); can = 0; }
+        }
+        const uint32_t *src_t = ci->d_table;
+        const uint8_t *src_f = ci->d_flags;
+        const fkb_partials *src_p = ci->d_partials;
+        cudaError_t e = cudaSuccess;
+        if (!can) {  // no peer mapping: stage the shard's accumulators on devices[0]
+            const size_t tb = fkb_table_entries(k) * sizeof(uint32_t), fb = fkb_prefix_flags_bytes(k);
+            if (!tmp_table) {
+                e = cudaMalloc(&tmp_table, tb);
+                if (e == cudaSuccess) e = cudaMalloc(&tmp_flags, fb);
+                if (e == cudaSuccess) e = cudaMalloc(&tmp_partials, sizeof(fkb_partials));
+            }
+            if (e == cudaSuccess) e = cudaMemcpyPeerAsync(tmp_table, c0->device, ci->d_table, ci->device, tb, c0->s_pipe);
+            if (e == cudaSuccess) e = cudaMemcpyPeerAsync(tmp_flags, c0->device, ci->d_flags, ci->device, fb, c0->s_pipe);
+            if (e == cudaSuccess) e = cudaMemcpyPeerAsync(tmp_partials, c0->device, ci->d_partials, ci->device, sizeof(fkb_partials), c0->s_pipe);
+            src_t = tmp_table; src_f = tmp_flags; src_p = tmp_partials;
+        }
+        int launches = 0;
+        if (e == cudaSuccess) e = fkb::launch_accumulate(launch_info(c0), k, c0->d_table, src_t, c0->d_flags, src_f, c0->d_partials, src_p, c0->s_pipe, &launches);
+        c0->launches += launches;
+        if (e == cudaSuccess && !can) e = cudaStreamSynchronize(c0->s_pipe);  // the staging buffers are reused by the next shard
+        if (e != cudaSuccess) {
+            say(cudaGetErrorString(e));
+            status = FKB_ERR_CUDA;
+        }
+    }
+    if (status == FKB_OK) {
+        status = finish_host(c0, k, stream_bytes, table, counts);
+        if (status != FKB_OK) say(fkb_last_error(c0));
+    }
+    if (tmp_table) cudaFree(tmp_table);
+    if (tmp_flags) cudaFree(tmp_flags);
+    if (tmp_partials) cudaFree(tmp_partials);
+    cleanup();
+    return status;
+}
+
+int fkb_count_file_gpus(const int *devices, int n_devices, const char *path, int k, uint32_t *table, fkb_counts *counts, char *err, size_t err_len)
+{
+    if (!path) return FKB_ERR_BAD_ARG;
+    const uint8_t *map = nullptr;
+    size_t len = 0;
+    fkb_context tmp;  // only its error string is used
+    if (int s = with_mapped_file(&tmp, path, &map, &len)) {
+        if (err && err_len) snprintf(err, err_len, "%s", tmp.err.c_str());
+        return s;
+    }
+    int s = fkb_count_fasta_host_gpus(devices, n_devices, map, len, k, table, counts, err, err_len);
+    munmap((void *)map, len);
+    return s;
+}
+
+int fkb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
 }
 
 // ---- synthetic inputs ----------------------------------------------------------------------------

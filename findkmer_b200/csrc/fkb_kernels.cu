@@ -502,20 +502,24 @@ cudaError_t launch_count(const LaunchInfo &li, const uint8_t *d_stream, uint64_t
                                        [&] { return launch_count_smallk(li, d_stream, lo, hi, k, d_table, d_flags, d_partials, st, launches); });
         return launch_direct(li, d_stream, begin, end, 0, 0, k, d_table, d_flags, d_partials, st, launches);
     }
-    const uint64_t unit = bucket_unit_bytes(k);
-    bool bucket = unit && li.bucket.gbuf && li.variant != VARIANT_DIRECT && li.variant != VARIANT_SMEM;
-    if (bucket && !bucket_folds_in_shared(k) && !(li.bucket.table_w && li.bucket.fold)) bucket = false;  // k <= 8 needs the W-mer table and the fold scratch
+    // k = 11 (AUTO or forced): 16-mer items counted as two 13-mers (fkb_bucket2.cu); VARIANT_BUCKET keeps the 13-mer path of fkb_bucket.cu
+    const bool fmt16 = bucket16_unit_bytes(k) != 0 && (li.variant == VARIANT_AUTO || li.variant == VARIANT_BUCKET16);
+    const uint64_t unit = fmt16 ? bucket16_unit_bytes(k) : bucket_unit_bytes(k);
+    bool bucket = unit && li.bucket.gbuf && li.variant != VARIANT_DIRECT && li.variant != VARIANT_SMEM && (fmt16 || li.variant != VARIANT_BUCKET16);
+    if (bucket && !fmt16 && !bucket_folds_in_shared(k) && !(li.bucket.table_w && li.bucket.fold)) bucket = false;  // k <= 8 needs the W-mer table and the fold scratch
     uint64_t lo = 0, hi = 0;
     if (bucket) {
         // interior [lo, hi): whole units, aligned in absolute stream coordinates, 16 readable bytes on both sides
         lo = (begin + 16 + unit - 1) / unit * unit;
         hi = end >= 16 ? (end - 16) / unit * unit : 0;
-        const uint64_t min_bytes = li.variant == VARIANT_BUCKET ? unit : bucket_min_bytes(k);
+        const uint64_t min_bytes = (li.variant == VARIANT_BUCKET || li.variant == VARIANT_BUCKET16) ? unit : bucket_min_bytes(k);
         bucket = hi > lo && hi - lo >= min_bytes;
     }
     if (!bucket) return launch_direct(li, d_stream, begin, end, 0, 0, k, d_table, d_flags, d_partials, st, launches);
-    return launch_with_slivers(li, d_stream, begin, lo, hi, end, k, d_table, d_flags, d_partials, st, launches,
-                               [&] { return launch_count_bucketed(li, li.bucket, d_stream, lo, hi, k, d_table, d_flags, d_partials, st, launches); });
+    return launch_with_slivers(li, d_stream, begin, lo, hi, end, k, d_table, d_flags, d_partials, st, launches, [&] {
+        return fmt16 ? launch_count_bucketed16(li, li.bucket, d_stream, lo, hi, d_table, d_flags, d_partials, st, launches)
+                     : launch_count_bucketed(li, li.bucket, d_stream, lo, hi, k, d_table, d_flags, d_partials, st, launches);
+    });
 }
 
 cudaError_t launch_finalize(const LaunchInfo &li, int k, const uint32_t *d_table, uint8_t *d_flags, const fkb_partials *d_partials,
@@ -532,6 +536,44 @@ cudaError_t launch_finalize(const LaunchInfo &li, int k, const uint32_t *d_table
             finalize_levels_kernel<false><<<grid, kThreads, 0, st>>>(d_table, k, d_in, d_flags, d_scratch, is_last, d_partials, stream_bytes, d_counts);
         if (launches) ++*launches;
     }
+    return cudaGetLastError();
+}
+
+// dst += src for the three accumulators of a shard (table: sums; prefix flags: OR; partials: sums).  src may be PEER memory
+// (another GPU of the box, mapped over NVLink): the multi-GPU exchange step of fkb_count_fasta_host_gpus.
+__global__ void __launch_bounds__(kThreads) accumulate_kernel(uint32_t *__restrict__ dst_table, const uint32_t *__restrict__ src_table, uint64_t n_table,
+                                                              uint8_t *__restrict__ dst_flags, const uint8_t *__restrict__ src_flags, uint64_t n_flags,
+                                                              fkb_partials *__restrict__ dst_p, const fkb_partials *__restrict__ src_p)
+{
+    const uint64_t tid = (uint64_t)blockIdx.x * kThreads + threadIdx.x, nth = (uint64_t)gridDim.x * kThreads;
+    const uint64_t n4 = n_table / 4;
+    for (uint64_t i = tid; i < n4; i += nth) {
+        const uint4 a = reinterpret_cast<const uint4 *>(src_table)[i];
+        uint4 d = reinterpret_cast<uint4 *>(dst_table)[i];
+        d.x += a.x; d.y += a.y; d.z += a.z; d.w += a.w;
+        reinterpret_cast<uint4 *>(dst_table)[i] = d;
+    }
+    for (uint64_t i = n4 * 4 + tid; i < n_table; i += nth) dst_table[i] += src_table[i];
+    const uint64_t f16 = n_flags / 16;  // both flag arrays come from cudaMalloc: 16-byte aligned
+    for (uint64_t i = tid; i < f16; i += nth) {
+        const uint4 a = reinterpret_cast<const uint4 *>(src_flags)[i];
+        uint4 d = reinterpret_cast<uint4 *>(dst_flags)[i];
+        d.x |= a.x; d.y |= a.y; d.z |= a.z; d.w |= a.w;
+        reinterpret_cast<uint4 *>(dst_flags)[i] = d;
+    }
+    for (uint64_t i = f16 * 16 + tid; i < n_flags; i += nth) dst_flags[i] |= src_flags[i];
+    if (tid < sizeof(fkb_partials) / sizeof(unsigned long long))
+        reinterpret_cast<unsigned long long *>(dst_p)[tid] += reinterpret_cast<const unsigned long long *>(src_p)[tid];
+}
+
+cudaError_t launch_accumulate(const LaunchInfo &li, int k, uint32_t *dst_table, const uint32_t *src_table, uint8_t *dst_flags, const uint8_t *src_flags,
+                              fkb_partials *dst_p, const fkb_partials *src_p, cudaStream_t st, int *launches)
+{
+    const uint64_t n_table = 1ull << (2 * k);
+    uint64_t n_flags = ((1ull << (2 * k)) - 4) / 3;
+    if (n_flags < 16) n_flags = 16;
+    accumulate_kernel<<<grid_for((n_table + 3) / 4, li.sm_count, 8), kThreads, 0, st>>>(dst_table, src_table, n_table, dst_flags, src_flags, n_flags, dst_p, src_p);
+    if (launches) ++*launches;
     return cudaGetLastError();
 }
 

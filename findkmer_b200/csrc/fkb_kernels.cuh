@@ -12,6 +12,7 @@ enum CountVariant : int {
     VARIANT_DIRECT = 1,   // fused encode + one red.global per window into the L2-resident table
     VARIANT_BUCKET = 2,   // W-mers at stride S routed through shared memory to per-bucket smem counters, then folded
     VARIANT_SMEM = 3,     // k <= 8: single pass, the whole 4^k table privatised per CTA in shared memory (fkb_smallk.cu)
+    VARIANT_BUCKET16 = 4, // k = 11: 16-mers at stride 6 routed as 32-bit items, counted twice (two 13-mers) in 8-bit counters (fkb_bucket2.cu)
 };
 
 // device scratch of VARIANT_BUCKET (owned by the context)
@@ -46,6 +47,11 @@ int bucket_segments_per_sm();  // pass-1 CTAs per SM (each owns one segment per 
 cudaError_t launch_count_bucketed(const LaunchInfo &li, const BucketScratch &bs, const uint8_t *d_stream, uint64_t lo, uint64_t hi, int k,
                                   uint32_t *d_table, uint8_t *d_flags, fkb_partials *d_partials, cudaStream_t st, int *launches);
 
+// k = 11, "double 13-mer" items (fkb_bucket2.cu); uses the same scratch as launch_count_bucketed
+uint64_t bucket16_unit_bytes(int k);  // interior granularity, 0 when the path does not support k
+cudaError_t launch_count_bucketed16(const LaunchInfo &li, const BucketScratch &bs, const uint8_t *d_stream, uint64_t lo, uint64_t hi, uint32_t *d_table,
+                                    uint8_t *d_flags, fkb_partials *d_partials, cudaStream_t st, int *launches);
+
 // single-pass shared-memory path for k <= 8 (fkb_smallk.cu)
 uint64_t smallk_unit_bytes(int k);   // interior granularity (one warp iteration), 0 when k > 8
 cudaError_t launch_count_smallk(const LaunchInfo &li, const uint8_t *d_stream, uint64_t lo, uint64_t hi, int k, uint32_t *d_table, uint8_t *d_flags,
@@ -58,6 +64,10 @@ cudaError_t launch_count(const LaunchInfo &li, const uint8_t *d_stream, uint64_t
 cudaError_t launch_finalize(const LaunchInfo &li, int k, const uint32_t *d_table, uint8_t *d_flags,
                             const fkb_partials *d_partials, uint64_t stream_bytes, fkb_counts *d_counts,
                             unsigned long long *d_scratch, cudaStream_t st, int *launches);
+
+// dst accumulators += src accumulators (src may be peer memory of another GPU): table sum, flags OR, partials sum
+cudaError_t launch_accumulate(const LaunchInfo &li, int k, uint32_t *dst_table, const uint32_t *src_table, uint8_t *dst_flags, const uint8_t *src_flags,
+                              fkb_partials *dst_p, const fkb_partials *src_p, cudaStream_t st, int *launches);
 
 cudaError_t launch_synth(const LaunchInfo &li, uint8_t *d_out, uint64_t first_byte, uint64_t n_bytes, int n_records,
                          const uint64_t *d_rec_offsets, const uint64_t *d_rec_base0, const uint8_t *d_headers,

@@ -38,9 +38,8 @@ template <int K> struct SmCfg {
     static constexpr int kGroups = kPacked ? 1 : 2;
 };
 
-// shared-memory reductions (no return value).  ptxas turns a PREDICATED shared atomic into a branch around it (BSSY / BRA /
-// ATOMS / BSYNC per item), so the general path adds 0 instead of skipping.
-__device__ __forceinline__ void reds_add(uint32_t saddr, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
+// shared-memory reduction (no return value).  ptxas turns a PREDICATED shared atomic into a branch around it (BSSY / BRA /
+// ATOMS / BSYNC per item), so the general path redirects an item that is not a window to a junk word instead of skipping it.
 __device__ __forceinline__ void reds_inc(uint32_t saddr) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(saddr) : "memory"); }
 __device__ __forceinline__ uint32_t atoms_add(uint32_t saddr, uint32_t v)
 {

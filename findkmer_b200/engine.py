@@ -261,6 +261,27 @@ class KmerCounter:
         return sb.value, (None if stop.value == (1 << 64) - 1 else stop.value), bool(eih.value)
 
 
+def device_count() -> int:
+    return int(_lib.load().fkb_device_count())
+
+
+def count_fasta_gpus(data, k: int, devices) -> KmerCounts:
+    """Raw file bytes -> counts on several GPUs of this box (contiguous shards, one host thread and one context per GPU, the
+    per-GPU tables summed on devices[0] over NVLink peer access) -- all inside the C library (fkb_count_fasta_host_gpus)."""
+    lib = _lib.load()
+    if not (1 <= k <= _lib.FKB_MAX_K):
+        raise FindKmerError(_lib.FKB_ERR_BAD_K, f"{k} is not a valid value for k")
+    addr, n, keep = _host_view(data)
+    devs = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+    table = np.empty(4 ** k, dtype=np.uint32)
+    counts = FkbCounts()
+    err = ctypes.create_string_buffer(512)
+    status = lib.fkb_count_fasta_host_gpus(devs, len(devices), addr, n, k, table.ctypes.data, ctypes.byref(counts), err, len(err))
+    if status != _lib.FKB_OK:
+        raise FindKmerError(status, err.value.decode() or _lib.status_string(status))
+    return KmerCounts.from_struct(k, table, counts)
+
+
 # ------------------------------------------------------------------------------------------------
 # writers (host C++ behind the ABI): statistics() and histo_recursive() of the reference
 # ------------------------------------------------------------------------------------------------

@@ -159,6 +159,19 @@ int fkb_count_file_multi(fkb_context *ctx, const char *path, const int *ks, int 
 /* same, reading the file itself: the reference's `-p <file>` (:416-428, :344) */
 int fkb_count_file(fkb_context *ctx, const char *path, int k, uint32_t *table, fkb_counts *counts);
 
+/* ---- several GPUs of one box (no context argument: one context per device is created and destroyed inside) ----
+ * The file image is cut into n_devices contiguous byte ranges; one host thread per GPU counts its range through the host
+ * pipeline (16-byte left halo from the look-back context, exactly as fkb_count_fasta_host_range); devices[0] then adds the
+ * other GPUs' tables / prefix flags / partials -- reading them from peer memory over NVLink where the devices can map each
+ * other, through a staging copy otherwise -- finalizes and returns table and counts as fkb_count_fasta_host does.
+ * The reference has no counterpart (its parallelism is one process per k, k6thru11fullANDupstream.sh:16-24); results are
+ * bit-identical to the single-GPU call.  err/err_len: optional buffer for the text of a failure. */
+int fkb_count_fasta_host_gpus(const int *devices, int n_devices, const uint8_t *fasta, size_t len, int k, uint32_t *table,
+                              fkb_counts *counts, char *err, size_t err_len);
+int fkb_count_file_gpus(const int *devices, int n_devices, const char *path, int k, uint32_t *table, fkb_counts *counts,
+                        char *err, size_t err_len);
+int fkb_device_count(void); /* usable CUDA devices (0 when there is none) */
+
 /* ---- writers: statistics() (:491-565) and histo_recursive() (:699-942) on the dense table -----
  * Byte-identical files to the reference's (x87 long double arithmetic, same expression order).
  * max_nodes = estimate_RAM_usage()'s return value, 1 + sum_{n=1..k} 4^n (:1256-1260). */

@@ -4,9 +4,11 @@ from dataclasses import replace
 from findkmer_b200 import synth
 from findkmer_b200.engine import KmerCounter
 c = KmerCounter(0); lib, ctx = c._lib, c._ctx
+if len(sys.argv) > 1: c.set_variant(int(sys.argv[1]))   # 2 = 13-mer buckets, 4 = 16-mer items (k = 11)
+sizes = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else (388_000_000, 775_000_000, 3_100_000_000)
 st = torch.cuda.current_stream()
 lib.fkb_set_option(ctx, b"phase_events", 1)
-for n in (388_000_000, 775_000_000, 3_100_000_000):
+for n in sizes:
     d = c.synth_fasta_device(replace(synth.config4(), n_bases=n).stripped())
     for k in (11,):
         acc = c.new_accumulators(k); acc_ms=[0,0,0]; tot=0

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Device-resident count throughput for the BASELINE.json shapes and k = 6..11 (not the bench line: evidence for DESIGN.md).
     python profiles/tools/sweep.py [shape-substring [k,k,... [n_bases [variant,variant,...]]]] > profiles/rNN_sweep.txt
-variants: 0 auto, 1 direct, 2 bucketed, 3 single-pass shared memory (k <= 8)"""
+variants: 0 auto, 1 direct, 2 bucketed (13-mers), 3 single-pass shared memory (k <= 8), 4 bucketed 16-mer items (k = 11)"""
 import sys
 from pathlib import Path
 
@@ -31,7 +31,7 @@ for name, lay in shapes:
         acc = c.new_accumulators(k)
         variants = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else ((0,) if n > (1 << 28) else (1, 2))
         for variant in variants:
-            if variant == 3 and k > 8:
+            if (variant == 3 and k > 8) or (variant == 4 and k != 11):
                 continue
             c.set_variant(variant)
             times = []
@@ -44,7 +44,7 @@ for name, lay in shapes:
                 torch.cuda.synchronize()
                 times.append(e0.elapsed_time(e1))
             ms = sorted(times[2:])[len(times[2:]) // 2]
-            print(f"{name:40s} {k:3d} {['auto', 'direct', 'bucketed', 'smem'][variant]:>8s} {ms:9.3f} {lay.n_bases / ms / 1e6:10.1f}")
+            print(f"{name:40s} {k:3d} {['auto', 'direct', 'bucketed', 'smem', 'bucket16'][variant]:>8s} {ms:9.3f} {lay.n_bases / ms / 1e6:10.1f}")
         c.set_variant(0)
         del acc
     del d

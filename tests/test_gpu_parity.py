@@ -241,6 +241,65 @@ def test_bucketed_variant_skewed_composition_uses_the_back_region(bucketed, harn
     assert_counts_equal(got, harness.oracle_count_stream(s, k))
 
 
+# ---- k = 11: 16-mer items counted as two 13-mers in 8-bit counters (fkb_bucket2.cu) ----------------------------
+@pytest.fixture()
+def bucket16(counter):
+    counter.set_variant(4)
+    yield counter
+    counter.set_variant(0)
+
+
+def test_bucket16_variant_matches_oracle(bucket16, harness):
+    """config-5 shape (many resets: the general path, left-over 11-mers, per-run events), whole and as three unaligned pieces;
+    clean sequence (the predicate-free path); 1001-base records; seeded junk"""
+    from findkmer_b200 import synth
+    k = 11
+    stream = bucket16.strip(synth.render(synth.config5(n_bases=1_500_000)))
+    want = harness.oracle_count_stream(stream, k)
+    launches0 = bucket16.launches
+    got, _ = _device_count(bucket16, stream, k)
+    assert bucket16.launches - launches0 >= 5  # edge slivers + bucketize16 + count_buckets16 + finalize levels
+    assert_counts_equal(got, want)
+    got, _ = _device_count(bucket16, stream, k, 12345, len(stream) - 777, pieces=3)
+    sub = harness.oracle_count_stream(stream[:len(stream) - 777], k)
+    head = harness.oracle_count_stream(stream[:12345], k)
+    assert np.array_equal(got.table, sub.table - head.table)
+    for lay in (synth.config2(n_bases=2_400_000), synth.config3(n_records=1500)):
+        stream = bucket16.strip(synth.render(lay))
+        got, _ = _device_count(bucket16, stream, k)
+        assert_counts_equal(got, harness.oracle_count_stream(stream, k))
+    for seed in range(3):
+        stream = bucket16.strip(random_fasta(seed, 400_000))
+        got, _ = _device_count(bucket16, stream, k)
+        assert_counts_equal(got, harness.oracle_count_stream(stream, k))
+
+
+def test_bucket16_variant_skewed_inputs_stay_exact(bucket16, harness):
+    """(1) poly-A with sparse substitutions: one bucket takes almost everything -- staging rows overflow, the bucket's region
+    in HBM overflows, and the 8-bit counters of pass 2 wrap, so the bucket is recounted exactly; (2) A/T-rich i.i.d. sequence:
+    hot buckets use the back region and hot counters drain at 0x80 into the per-bucket list; (3) a tandem repeat of period 7."""
+    k = 11
+    rng = np.random.default_rng(3)
+    s = np.full(3_000_000, ord("A"), dtype=np.uint8)
+    idx = rng.integers(0, s.size, size=6000)
+    s[idx] = np.frombuffer(b"CGTN", dtype=np.uint8)[rng.integers(0, 4, size=idx.size)]
+    got, _ = _device_count(bucket16, s, k)
+    want = harness.oracle_count_stream(s, k)
+    assert int(want.table.max()) > 100_000
+    assert_counts_equal(got, want)
+    rng = np.random.default_rng(11)
+    s = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.choice(4, size=8_000_000, p=[0.4, 0.1, 0.1, 0.4])].copy()
+    s[rng.integers(0, s.size, size=300)] = ord("N")
+    got, _ = _device_count(bucket16, s, k)
+    want = harness.oracle_count_stream(s, k)
+    assert int(want.table.max()) > 300          # counters beyond 0x80: the drain list is exercised
+    assert_counts_equal(got, want)
+    s = np.tile(np.frombuffer(b"ACGGTCA", dtype=np.uint8), 400_000)
+    s[rng.integers(0, s.size, size=500)] = ord("T")
+    got, _ = _device_count(bucket16, s, k)
+    assert_counts_equal(got, harness.oracle_count_stream(s, k))
+
+
 # ---- k <= 8: the single-pass shared-memory path (fkb_smallk.cu) ------------------------------------------------
 @pytest.fixture()
 def smem_path(counter):
@@ -631,6 +690,41 @@ def test_large_soft_masked_bucketed_equals_direct(counter):
         del acc, acc2
     del d
     torch.cuda.empty_cache()
+
+
+# ---- several GPUs behind the C boundary (skipped on a one-GPU box) --------------------------------------------
+def test_multi_gpu_c_abi_and_cli(harness, tmp_path):
+    """fkb_count_fasta_host_gpus / `findKmer -g N`: contiguous shards on N GPUs, tables summed on GPU 0 over peer access --
+    bit-identical to the oracle (and the CLI's files byte-identical to the reference binary's), cuts falling anywhere (inside
+    header lines, inside N runs), a terminating byte 0xFF in the middle shard, every k path."""
+    import subprocess
+    from conftest import ROOT
+    from findkmer_b200 import synth
+    from findkmer_b200.engine import count_fasta_gpus, device_count
+    n_dev = device_count()
+    if n_dev < 2:
+        pytest.skip("needs at least two GPUs")
+    devices = list(range(min(n_dev, 4)))
+    data = synth.render(synth.config5(n_bases=3_000_000))
+    for k in (6, 8, 11, 13):
+        assert_counts_equal(count_fasta_gpus(data, k, devices), harness.oracle_count_fasta(data, k))
+    assert_counts_equal(count_fasta_gpus(data, 11, devices[:2]), harness.oracle_count_fasta(data, 11))
+    big = synth.render(synth.config4(n_bases=60_000_000))  # large enough for the bucketed kernels on every shard
+    assert_counts_equal(count_fasta_gpus(big, 11, devices[:2]), harness.oracle_count_fasta(big, 11))
+    records = synth.render(synth.config3(n_records=3000))  # a header line every kilobase: cuts land inside headers
+    assert_counts_equal(count_fasta_gpus(records, 9, devices), harness.oracle_count_fasta(records, 9))
+    stopped = data.copy()
+    stopped[len(stopped) // 2 + 12345] = 0xFF  # ends the scan in a middle shard: later shards must count nothing
+    assert_counts_equal(count_fasta_gpus(stopped, 8, devices), harness.oracle_count_fasta(stopped, 8))
+    exe = ROOT / "findkmer_b200" / "bin" / "findKmer"
+    if exe.exists() and harness.reference_available():
+        ref = harness.run_reference(data, 8, name="genome.fa")
+        data.tofile(tmp_path / "genome.fa")
+        run = subprocess.run([str(exe), "-q", "1", "-k", "8", "-g", str(len(devices)), "-p", "genome.fa"], cwd=tmp_path, capture_output=True,
+                             text=True, timeout=300)
+        assert run.returncode == 0, run.stderr[-500:]
+        assert (tmp_path / ref.csv_name).read_bytes() == ref.csv
+        assert (tmp_path / ref.stats_name).read_bytes() == ref.stats
 
 
 # ---- the drop-in program against the untouched reference binary ---------------------------------------------
