@@ -43,11 +43,13 @@ constexpr int kItems = kCH / kStep;    // 8
 constexpr uint64_t kWSpan = 32ull * kCH;
 constexpr int kNB = 1024;              // buckets
 constexpr int kCap = 52;               // staged items per bucket: 13 chunks of 4 items = 208 bytes per row, as in fkb_bucket.cu
+// pass-1 CTA size and tile length, measured on B200 (profiles/r02_b16_variants.txt, config 4): 512 threads x 7 iterations 1.44 ms,
+// 576 x 6 1.42, 640 x 6 1.39 (102 registers: the last size without spills), 768 x 5 1.55, 1024 x 3 2.27 (64 registers: spills)
 #ifndef FKB2_P1_THREADS
-#define FKB2_P1_THREADS 512
+#define FKB2_P1_THREADS 640
 #endif
 #ifndef FKB2_TILE_ITERS
-#define FKB2_TILE_ITERS 7              // warp iterations between flushes: 7 * 8 * 512 / 1024 = 28 items per row on average (+ <= 3 carried) of 52
+#define FKB2_TILE_ITERS 6              // warp iterations between flushes: 6 * 8 * 640 / 1024 = 30 items per row on average (+ <= 3 carried) of 52
 #endif
 #ifndef FKB2_P2_THREADS
 #define FKB2_P2_THREADS 1024
@@ -252,7 +254,11 @@ bucketize16_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers
                     f[n] = item_at<n>(grp);
                     bk[n] = bucket_of(f[n]);
                     const uint32_t ca = mad_u32(bk[n], 4u, cursor_sa);
+#ifdef FKB2_EXP_NOSTAGE  // (profiling experiment: no slot atomics, no payload stores -- loads + encode + loop overhead alone)
+                    if constexpr (ALL) pos[n] = (ca & 1u) ? atoms_inc(ca) : 0xFFFFFFFFu;
+#else
                     if constexpr (ALL) pos[n] = atoms_inc(ca);
+#endif
                     else {
                         const uint32_t e = emit[ItemPos<n>::g] & (1u << (15 - ItemPos<n>::i));
                         const uint32_t ps = atoms_inc(e ? ca : cursor_sa + 4u * (uint32_t)(kNB + lane));
@@ -347,8 +353,12 @@ bucketize16_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers
                     for (int j = 0; j < 4; ++j) {
                         const uint32_t ncb = (pk[j] >> 28) << 2, offb = (pk[j] & 0x0FFFFFFFu) << 2;
                         uint32_t *dst = my_gbuf + (uint64_t)(b0 + 4 * (jj + j) + sub) * bstride + offb + c * 4u;
+#ifndef FKB2_EXP_NOFLUSH  // (profiling experiment, profiles/r02_b16_experiments.txt: without the flush stores the results are wrong and the time is the compute phase alone)
                         stg128_if(dst, v[2 * j], c * 4u < ncb);
                         stg128_if(dst + 32, v[2 * j + 1], c * 4u + 32u < ncb);
+#else
+                        if (v[2 * j].x == 0x12345u && v[2 * j + 1].y == 0x54321u) stg128_if(dst, v[2 * j], c * 4u < ncb);
+#endif
                     }
                 }
                 __syncwarp();

@@ -9,6 +9,8 @@
 //   mode 1  cp.async.cg.shared.global 16 B (LDGSTS) into a 3-stage shared-memory ring, cp.async.wait_group, ld.shared.v4
 //   mode 2  cp.async.bulk.shared::cluster.global (1-D TMA) of a whole 16 KiB tile by ONE thread into the ring, completion on an
 //           mbarrier (expect_tx), consumers spin on mbarrier.try_wait.parity, ld.shared.v4
+//   mode 3  as mode 0, but with the count kernels' work distribution: one contiguous region per WARP (thousands of concurrent
+//           streams) instead of 16 KiB tiles handed out round-robin to the CTAs (one moving window over the stream)
 // Output: one JSON line per (mode, work, CTAs per SM): {"bench":"stage","mode":..,"work":..,"ctas_per_sm":..,"gbs":..}
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -63,6 +65,24 @@ __global__ void __launch_bounds__(kThreads) stream_kernel(const uint8_t *__restr
             const uint64_t tn = t + gridDim.x;
 #pragma unroll
             for (int g = 0; g < 4; ++g) nxt[g] = ldg128_if(s + tn * kTile + threadIdx.x * kPerThread + 16 * g, tn < n_tiles);
+            consume<WORK>(cur, acc, va);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) cur[g] = nxt[g];
+        }
+    } else if constexpr (MODE == 3) {
+        // the count kernels' work distribution: every WARP streams its own contiguous region (lane = 64 consecutive bytes, warp
+        // iteration = 2 KiB), so thousands of separate streams are open at the same time
+        const uint64_t n_wit = n_tiles * (kTile / 2048), n_warps = (uint64_t)gridDim.x * (kThreads / 32);
+        const uint64_t gw = (uint64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+        const uint64_t q = n_wit / n_warps, first = gw * q, iters = (gw + 1 == n_warps) ? n_wit - first : q;
+        const uint8_t *base = s + first * 2048 + (threadIdx.x & 31) * kPerThread;
+        uint4 cur[4], nxt[4];
+        if (iters)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) cur[g] = ldg128(base + 16 * g);
+        for (uint64_t it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) nxt[g] = ldg128_if(base + (it + 1) * 2048 + 16 * g, it + 1 < iters);
             consume<WORK>(cur, acc, va);
 #pragma unroll
             for (int g = 0; g < 4; ++g) cur[g] = nxt[g];
@@ -135,8 +155,8 @@ template <int MODE, bool WORK>
 static void run(const uint8_t *d, uint64_t n_bytes, uint32_t *out, int sm_count, int ctas_per_sm)
 {
     const uint64_t n_tiles = n_bytes / kTile;
-    const int smem = MODE == 0 ? 0 : kStages * (int)kTile;
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(stream_kernel<MODE, WORK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int smem = (MODE == 0 || MODE == 3) ? 0 : kStages * (int)kTile;
+    if (smem > 32 * 1024) CK(cudaFuncSetAttribute(stream_kernel<MODE, WORK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
@@ -171,11 +191,13 @@ int main(int argc, char **argv)
         if (only_ctas && ctas != only_ctas) continue;
         if (ctas * kStages * (int)kTile > 200 * 1024) {  // the ring of modes 1 and 2 limits residency: 4 CTAs of 48 KiB per SM
             if (only_mode <= 0) { run<0, true>(d, n_bytes, out, prop.multiProcessorCount, ctas); run<0, false>(d, n_bytes, out, prop.multiProcessorCount, ctas); }
+            if (only_mode < 0 || only_mode == 3) { run<3, true>(d, n_bytes, out, prop.multiProcessorCount, ctas); run<3, false>(d, n_bytes, out, prop.multiProcessorCount, ctas); }
             continue;
         }
         if (only_mode < 0 || only_mode == 0) { run<0, true>(d, n_bytes, out, prop.multiProcessorCount, ctas); run<0, false>(d, n_bytes, out, prop.multiProcessorCount, ctas); }
         if (only_mode < 0 || only_mode == 1) { run<1, true>(d, n_bytes, out, prop.multiProcessorCount, ctas); run<1, false>(d, n_bytes, out, prop.multiProcessorCount, ctas); }
         if (only_mode < 0 || only_mode == 2) { run<2, true>(d, n_bytes, out, prop.multiProcessorCount, ctas); run<2, false>(d, n_bytes, out, prop.multiProcessorCount, ctas); }
+        if (only_mode < 0 || only_mode == 3) { run<3, true>(d, n_bytes, out, prop.multiProcessorCount, ctas); run<3, false>(d, n_bytes, out, prop.multiProcessorCount, ctas); }
     }
     return 0;
 }

@@ -37,9 +37,9 @@ def main():
             infn = mangled in ln
         if not infn:
             continue
-        m = re.search(r'//## File ".*?%s", line (\d+)' % re.escape(src.name), ln)
-        if m:
-            cur = int(m.group(1))
+        m = re.search(r'//## File "(.*?)", line (\d+)', ln)
+        if m:  # code inlined from a header keeps its own (file, line)
+            cur = (Path(m.group(1)).name, int(m.group(2)))
             continue
         m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
         if m:
@@ -69,12 +69,23 @@ def main():
         samples[line] += smp
         tot += n
         stot += smp
-    text = (ROOT / src).read_text().split("\n") if (ROOT / src).exists() else src.read_text().split("\n")
+    texts = {}
+
+    def source_line(key):
+        if not key:
+            return "(no line info)"
+        name, line = key
+        if name not in texts:
+            cands = [ROOT / src] + list((ROOT / "findkmer_b200" / "csrc").glob(name))
+            hit = [c for c in cands if c.name == name and c.exists()]
+            texts[name] = hit[0].read_text().split("\n") if hit else []
+        t = texts[name]
+        return (t[line - 1].strip()[:100] if 0 < line <= len(t) else "?")
     print(f"kernel {mangled}: {tot:.0f} warp-level instructions executed, {stot:.0f} stall samples")
-    print(f"{'instr%':>7} {'stall%':>7}  line  source")
+    print(f"{'instr%':>7} {'stall%':>7}  file:line  source")
     for line, n in by_line.most_common(top):
-        s = text[line - 1].strip()[:110] if line else "(no line info)"
-        print(f"{n / tot * 100:7.2f} {samples[line] / max(stot, 1) * 100:7.2f}  {line!s:>4}  {s}")
+        where = f"{line[0]}:{line[1]}" if line else "-"
+        print(f"{n / tot * 100:7.2f} {samples[line] / max(stot, 1) * 100:7.2f}  {where:>22}  {source_line(line)}")
 
 
 if __name__ == "__main__":
