@@ -23,7 +23,7 @@ def main():
     names = [launches[i]["kernel"] for i in ids]
     # a step = [bucketize, count_buckets, count_direct_kernel (the edge slivers, side stream), (fold levels), finalize levels]: take the last one
     # (the edge slivers' count_direct_kernel runs on a side stream and may be listed after the bucketed kernels)
-    starts = [i for i, n in zip(ids, names) if "bucketize_kernel" in n] or [i for i, n in zip(ids, names) if "count_direct_kernel" in n]
+    starts = [i for i, n in zip(ids, names) if "bucketize" in n] or [i for i, n in zip(ids, names) if "count_direct_kernel" in n]
     if not starts:
         sys.exit("no count kernel launch in the capture")
     step = [i for i in ids if i >= starts[-1] and ("fkb" in launches[i]["kernel"] or "unnamed" in launches[i]["kernel"])]
