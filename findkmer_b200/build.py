@@ -75,12 +75,16 @@ def build(verbose: bool = False, force: bool = False) -> Path:
     return LIB
 
 
-def build_variant(name: str, defines, verbose: bool = False) -> Path:
-    """A tuning variant of the library (profiling only): same sources, extra -D flags, written to build/variants/."""
+def build_variant(name: str, defines, verbose: bool = False, only=None) -> Path:
+    """A tuning variant of the library (profiling only): same sources, extra -D flags, written to build/variants/.
+    `only`: the sources the flags matter for (the others are taken from the regular build)."""
     vdir = ROOT / "build" / "variants" / name
     vdir.mkdir(parents=True, exist_ok=True)
     objs = []
     for src in CU_SOURCES:
+        if only is not None and src not in only:
+            objs.append(OBJ / (src + ".o"))
+            continue
         o = vdir / (src + ".o")
         _run([NVCC] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-c", CSRC / src, "-o", o], verbose)
         objs.append(o)

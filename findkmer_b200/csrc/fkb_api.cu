@@ -524,6 +524,7 @@ int fkb_create(int device, fkb_context **out)
     }
     const char *v = getenv("FKB_VARIANT");
     ctx->forced_variant = v ? atoi(v) : 0;
+    if (const char *r = getenv("FKB_P1_RING")) ctx->bucket.p1_ring = r[0] == '1';
     const char *l = getenv("FKB_LOADER");
     ctx->loader_mode = l ? (!strcmp(l, "host") ? 1 : (!strcmp(l, "device") ? 2 : 0)) : 0;
     if (const char *ns = getenv("FKB_LOADER_SLOTS"))
@@ -614,6 +615,10 @@ int fkb_set_option(fkb_context *ctx, const char *name, long value)
     }
     if (!strcmp(name, "loader_slots") && value >= 2 && value <= fkb_context::kMaxSlots) {
         ctx->n_slots = (int)value;
+        return FKB_OK;
+    }
+    if (!strcmp(name, "p1_ring") && (value == 0 || value == 1)) {
+        ctx->bucket.p1_ring = (int)value;
         return FKB_OK;
     }
     if (!strcmp(name, "phase_events") && (value == 0 || value == 1)) {

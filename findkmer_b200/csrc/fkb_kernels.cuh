@@ -25,6 +25,7 @@ struct BucketScratch {
     uint32_t *work = nullptr;      // pass-2 work counter (word 0) and, from word 16 on, one item total per bucket
     uint16_t *table_w = nullptr;   // [4^W] 16-bit W-mer counts
     uint32_t *fold = nullptr;      // per-level (all, suf) arrays of the fold
+    int p1_ring = 0;               // option "p1_ring": k = 11 pass 1 with ring rows and an asynchronous, warp-distributed flush (fkb_bucket2.cu)
     cudaEvent_t phase_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // option "phase_events": before pass 1 / after pass 1 / after pass 2 / after the fold
 };
 

@@ -90,7 +90,9 @@ int fkb_device_info(fkb_context *ctx, int *sm_count, int *cc_major, int *cc_mino
  * 1 = always the host loader, 2 = always the device loader (FKB_LOADER=host|device).
  * "loader_chunk": raw bytes per device-loader chunk (0 = 128 MiB).
  * "loader_slots": 4 MiB pinned slots of the host loader's ring, 2..64 (default 24; FKB_LOADER_SLOTS).
- * "phase_events": 1 = record CUDA events around the kernels of the bucketed path (see fkb_phase_times). */
+ * "phase_events": 1 = record CUDA events around the kernels of the bucketed path (see fkb_phase_times).
+ * "p1_ring": 1 = the k = 11 path routes through ring-shaped staging rows that the warps flush asynchronously (an experiment
+ * kept for measurement: same counts, slower than the default synchronous flush; FKB_P1_RING=1 sets it at fkb_create time). */
 int fkb_set_option(fkb_context *ctx, const char *name, long value);
 /* Profiling aid (no counterpart in the reference): with option "phase_events" = 1 the bucketed count path records CUDA events
  * around its kernels; this returns the durations of the LAST such count call in milliseconds -- ms[0] pass 1 (bucketize),

@@ -242,10 +242,13 @@ def test_bucketed_variant_skewed_composition_uses_the_back_region(bucketed, harn
 
 
 # ---- k = 11: 16-mer items counted as two 13-mers in 8-bit counters (fkb_bucket2.cu) ----------------------------
-@pytest.fixture()
-def bucket16(counter):
+@pytest.fixture(params=[0, 1], ids=["sync_flush", "ring_flush"])
+def bucket16(counter, request):
+    """both forms of pass 1: the default (synchronous flush) and option "p1_ring" (ring rows flushed asynchronously by their owner warps)"""
     counter.set_variant(4)
+    counter._check(counter._lib.fkb_set_option(counter._ctx, b"p1_ring", request.param))
     yield counter
+    counter._check(counter._lib.fkb_set_option(counter._ctx, b"p1_ring", 0))
     counter.set_variant(0)
 
 
