@@ -24,6 +24,14 @@ constexpr int kChunk = 64;  // bytes owned per thread per iteration
 
 // sum_{e<d} 4^e = (4^d - 4) / 3; (4^d - 1) / 3 is the bit pattern 0101..01 (d ones): no division on the event path
 __host__ __device__ inline uint64_t flags_offset(int d) { return (0x5555555555555555ull & ((1ull << (2 * d)) - 1ull)) - 1ull; }  // sum_{e<d} 4^e
+// look before storing: every run start writes the same few flag bytes, and plain stores from 148 SMs onto one L2 line serialise
+// (fkb_stream.cuh set_flag has the measurement); flags only go 0 -> 1, so a stale 0 costs one redundant store
+__device__ __forceinline__ void set_flag(uint8_t *flag)
+{
+    uint32_t v;
+    asm volatile("ld.global.ca.u8 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v == 0) *flag = 1;
+}
 
 // 128-bit read-only load.  The stream is read once; neighbouring lanes share 32-byte sectors across the
 // five loads of an iteration, so L1 allocation is kept (no .no_allocate).
@@ -106,7 +114,7 @@ __device__ __noinline__ void rare_event(uint32_t kmer, int run, int k, uint8_t *
         atomicAdd(&ev[8], 1u);
     } else {  // 1 <= run < k
         uint32_t prefix = kmer & ((1u << (2 * run)) - 1u);
-        flags[flags_offset(run) + prefix] = 1;
+        set_flag(flags + flags_offset(run) + prefix);
         atomicAdd(&ev[4 + (prefix >> (2 * (run - 1)))], 1u);
     }
 }

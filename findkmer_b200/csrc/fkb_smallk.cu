@@ -77,7 +77,6 @@ count_smem_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers,
     __shared__ uint32_t ev[16];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t cnt_sa = (uint32_t)__cvta_generic_to_shared(cnt);
-    const uint32_t junk_sa = cnt_sa + SmCfg<K>::kTableBytes + 4u * (uint32_t)lane;  // one junk word per lane (one bank each), behind the table
 
     for (uint32_t i = threadIdx.x; i < SmCfg<K>::kTableBytes / 16; i += kThreads) reinterpret_cast<uint4 *>(cnt)[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x < 16) ev[threadIdx.x] = 0;
@@ -117,7 +116,7 @@ count_smem_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers,
                 }
                 if (va.bad()) {
 #pragma unroll
-                    for (int g = 0; g < kG; ++g) grp[g + 1] = pack_group(r0[g], t_unknown);
+                    for (int g = 0; g < kG; ++g) grp[g + 1].valid = exact_valid16(r0[g], t_unknown);
                 }
             }
             const uint32_t up_c = __shfl_sync(0xffffffffu, grp[kG].code, (lane + 31) & 31);
@@ -127,29 +126,34 @@ count_smem_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers,
             carry.code = up_c;   // lane 0: lane 31's last group = the bytes in front of the next iteration
             carry.valid = up_v;
 
-            uint32_t own = grp[0].valid;
+            // lane state.  WHOLE: my bytes and the K bytes in front of them are bases -- every window that ends in my chunk exists and
+            // none of them is the first of its run: the predicate-free count block below, no events.  Otherwise (a run boundary
+            // within reach, or no base at all) the lane skips that block; its windows and its per-run events go through the
+            // warp-cooperative handler, which adds a window straight to T_k with a global red (a few lanes per run boundary: ~1 %
+            // of the windows of config 5).
+            uint32_t own = 0xFFFFu;
 #pragma unroll
             for (int g = 1; g <= kG; ++g) own &= grp[g].valid;
-            const bool clean = __all_sync(0xffffffffu, own == 0xFFFFu);
-
-            uint32_t emit[kG + 1];
-            if (clean) {
+            constexpr uint32_t kCtx = (1u << K) - 1u;
+            const bool whole = own == 0xFFFFu && (grp[0].valid & kCtx) == kCtx;
+            if (__all_sync(0xffffffffu, whole)) {
                 ++n_fast;
-#pragma unroll
-                for (int g = 1; g <= kG; ++g) emit[g] = 0xFFFFu;
             } else {
-                // general path: per-position window masks; the rare per-run events are handled by the whole warp
+                if (whole) {
+                    t_windows += kCH;
+                    t_valid += kCH;
+                }
 #pragma unroll
                 for (int g = 1; g <= kG; ++g) {
                     const uint32_t m = (grp[g - 1].valid << 16) | grp[g].valid;
-                    const uint32_t rk = runs_of<K>(m) & 0xFFFFu;          // bit 15-i: a full window ends at byte i of the group
-                    emit[g] = rk;
+                    const uint32_t rk0 = runs_of<K>(m) & 0xFFFFu;               // bit 15-i: a full window ends at byte i of the group
+                    const uint32_t rk = whole ? 0u : rk0;
+                    const uint32_t first_k = rk & ~(m >> K) & 0xFFFFu;          // run length is exactly k here
+                    const uint32_t shorts = whole ? 0u : (grp[g].valid & ~rk0);  // valid base whose run is still shorter than k
                     t_windows += __popc(rk);
-                    t_valid += __popc(grp[g].valid);
-                    const uint32_t first_k = rk & ~(m >> K) & 0xFFFFu;    // run length is exactly k here
-                    const uint32_t shorts = grp[g].valid & ~rk;            // valid base whose run is still shorter than k
-                    const uint32_t who = __ballot_sync(0xffffffffu, (first_k | shorts) != 0);
-                    if (who) warp_group_events(who, 0u, first_k, shorts, m, grp[g - 1].code, grp[g].code, K, flags, ev, table_k);
+                    if (!whole) t_valid += __popc(grp[g].valid);
+                    const uint32_t who = __ballot_sync(0xffffffffu, (rk | shorts) != 0);
+                    if (who) warp_group_events(who, rk, first_k, shorts, m, grp[g - 1].code, grp[g].code, K, flags, ev, table_k);
                 }
             }
 
@@ -157,10 +161,8 @@ count_smem_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers,
 #pragma unroll
             for (int g = 0; g < kG; ++g) r0[g] = ldg128_if(lane_base + (uint64_t)(it + 1) * kWSpan + 16 * g, it + 1 < my_iters);
 
-            // the 16 windows of every group: one shared-memory atomic each, 8 back to back.  CLEAN (warp-uniform): every window
-            // exists, no predicates at all.
-            auto count_groups = [&](auto clean_t) {
-                constexpr bool CLEAN = decltype(clean_t)::value;
+            // the 16 windows of every group of a WHOLE lane: one shared-memory atomic each, 8 back to back, no predicates
+            if (whole) {
 #pragma unroll
                 for (int g = 1; g <= kG; ++g) {
 #pragma unroll
@@ -169,11 +171,7 @@ count_smem_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers,
 #pragma unroll
                             for (int i = 8 * h; i < 8 * h + 8; ++i) {
                                 const uint32_t f = (i == 15) ? grp[g].code : __funnelshift_r(grp[g].code, grp[g - 1].code, 2 * (15 - i));
-                                uint32_t sa = mad_u32(f & MASK, 4u, cnt_sa);
-                                // no window here: the increment goes to this lane's junk word (a predicated shared atomic would become a
-                                // branch per item; adding 0 in place would pile the identical garbage windows of an N run onto one address)
-                                if constexpr (!CLEAN) sa = (emit[g] & (1u << (15 - i))) ? sa : junk_sa;
-                                reds_inc(sa);
+                                reds_inc(mad_u32(f & MASK, 4u, cnt_sa));
                             }
                         } else {
                             uint32_t f[8], old[8], any = 0;
@@ -181,13 +179,8 @@ count_smem_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers,
                             for (int i = 8 * h; i < 8 * h + 8; ++i) {
                                 const int j = i - 8 * h;
                                 f[j] = (i == 15) ? grp[g].code : __funnelshift_r(grp[g].code, grp[g - 1].code, 2 * (15 - i));
-                                uint32_t sa = mad_u32(f[j] & 0xFFFEu, 2u, cnt_sa);              // word of counters 2n, 2n+1
-                                uint32_t inc = mad_u32(f[j] & 1u, 0xFFFFu, 1u);                 // odd k-mer: the high half
-                                if constexpr (!CLEAN) {                                         // no window here: add nothing, to the junk word
-                                    const bool e = (emit[g] & (1u << (15 - i))) != 0;
-                                    sa = e ? sa : junk_sa;
-                                    inc = e ? inc : 0u;  // (so the junk words stay 0 and can never look like a counter at 0x8000 below)
-                                }
+                                const uint32_t sa = mad_u32(f[j] & 0xFFFEu, 2u, cnt_sa);   // word of counters 2n, 2n+1
+                                const uint32_t inc = mad_u32(f[j] & 1u, 0xFFFFu, 1u);      // odd k-mer: the high half
                                 old[j] = atoms_add(sa, inc);
                             }
 #pragma unroll
@@ -203,9 +196,7 @@ count_smem_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers,
                         }
                     }
                 }
-            };
-            if (clean) count_groups(std::true_type{});
-            else count_groups(std::false_type{});
+            }
         }
         // 32-bit event counters of this tile -> 64-bit partials
         __syncthreads();

@@ -111,6 +111,23 @@ __device__ __forceinline__ Group pack_group(const uint4 &g, uint32_t &unknown)
     return r;
 }
 
+// exact validity mask of 16 bytes (first byte = bit 15) WITHOUT the codes (the fast encode below already has them for every byte
+// that is a base); `unknown` accumulates the bytes outside {A,C,G,T,N,'>'} as pack_group does
+__device__ __forceinline__ uint32_t bad_bytes_word(uint32_t w)  // byte i is ZERO iff input byte i is one of A,C,G,T (see encode_word)
+{
+    const uint32_t p1 = shr_c<1>(w), p2 = shr_c<2>(w), p4 = shr_c<4>(w);
+    const uint32_t q = p2 & ~p1;
+    return ((w & 0xE8E8E8E8u) ^ 0x40404040u) | (((p4 ^ q) | ~(w ^ q)) & 0x01010101u);
+}
+__device__ __forceinline__ uint32_t exact_valid16(const uint4 &g, uint32_t &unknown)
+{
+    const uint32_t valid = (zero_bytes_nibble(bad_bytes_word(g.x)) << 12) | (zero_bytes_nibble(bad_bytes_word(g.y)) << 8) |
+                           (zero_bytes_nibble(bad_bytes_word(g.z)) << 4) | zero_bytes_nibble(bad_bytes_word(g.w));
+    const uint32_t nN = count_n_or_gt(g.x) + count_n_or_gt(g.y) + count_n_or_gt(g.z) + count_n_or_gt(g.w);
+    unknown += 16 - __popc(valid) - nN;
+    return valid;
+}
+
 // ---- fast encode: codes only; validity is ACCUMULATED over many words and tested once ----------------
 // A byte is one of A,C,G,T  <=>  b7 b6 b5 b3 = 0 1 0 0,  b4 == q,  b0 == ~q  with q = b2 & ~b1 (see encode_word).
 // The two relations are evaluated at bit 4 of every byte from LEFT-shifted copies of the word (left shifts are IMAD.SHL on
@@ -164,6 +181,17 @@ __device__ __forceinline__ uint32_t runs_of(uint32_t m)
     }
 }
 
+// A short run's prefix flag.  Flags only ever go from 0 to 1, and EVERY run start writes the same few bytes (depth 1..3 are 84
+// bytes: one line): plain stores from 148 SMs onto one L2 line serialise -- config 5 ran at 0.86 Tbases/s with them and at 1.70
+// without (profiles/r02_flag_stores.txt).  So look first: the load is served by the SM's L1 after the first miss; a stale 0 only
+// costs one redundant store (which drops the stale line), never a wrong flag.
+__device__ __forceinline__ void set_flag(uint8_t *flag)
+{
+    uint32_t v;
+    asm volatile("ld.global.ca.u8 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v == 0) *flag = 1;
+}
+
 // rare per-run events of one group (positions given as bits of 16-bit masks, first byte = bit 15).
 // ev[0..3] head_base, ev[4..7] short_first, ev[8] runs_ge_k: CTA-private counters in shared memory -- soft-masked /
 // N-rich genomes have millions of run boundaries, and global atomics on nine fixed addresses would serialise them.
@@ -202,7 +230,7 @@ __device__ __noinline__ void warp_group_events(uint32_t who, uint32_t left, uint
         if ((Sh >> b) & 1u) {  // valid base whose run is still shorter than k: the reference inserts a short path (:1059-1062)
             const int run = __ffs(~(M >> b)) - 1;  // consecutive valid bytes ending here (1 .. k-1)
             const uint32_t prefix = win & ((1u << (2 * run)) - 1u);
-            flags[flags_offset(run) + prefix] = 1;
+            set_flag(flags + flags_offset(run) + prefix);
             atomicAdd(&ev[4 + (prefix >> (2 * (run - 1)))], 1u);
         }
     }
