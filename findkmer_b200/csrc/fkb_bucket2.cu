@@ -814,7 +814,7 @@ struct P2Smem {
     uint32_t drain[kDrainCap];  // (array << 16) | index of every drained counter (128 counts each)
     uint2 fill[512];
     uint32_t key[kNB];
-    uint32_t bucket, next_seg, max_total, n_drain, overflow;
+    uint32_t bucket, next_seg, max_total, sum_total, n_drain, overflow;
 };
 
 // fold one array: out index o (12 bits) at offset t (0..2) of the array's 13-mer; R = number of low bits of o that lie below the core
@@ -873,29 +873,37 @@ count_buckets16_kernel(const uint32_t *__restrict__ gbuf, uint32_t cap_cb, uint3
     P2Smem &sm = *reinterpret_cast<P2Smem *>(smem_raw);
     const int lane = threadIdx.x & 31;
     const uint32_t cntA_sa = (uint32_t)__cvta_generic_to_shared(sm.cnt[0]), cntB_sa = cntA_sa + 65536u;
-    // largest buckets first (see fkb_bucket.cu)
+    // largest buckets first (see fkb_bucket.cu) -- unless the buckets are about equally full (uniform sequence: the largest within
+    // 25 % of the mean), where the order does not matter and the 55 barrier stages of the sort are 16 us of every CTA's time
     const uint32_t *bucket_total = work + 16;
-    if (threadIdx.x == 0) sm.max_total = 0;
+    if (threadIdx.x == 0) { sm.max_total = 0; sm.sum_total = 0; }
     __syncthreads();
-    for (int i = threadIdx.x; i < kNB; i += kP2Threads) atomicMax(&sm.max_total, bucket_total[i]);
+    for (int i = threadIdx.x; i < kNB; i += kP2Threads) {
+        const uint32_t t = bucket_total[i];
+        atomicMax(&sm.max_total, t);
+        atomicAdd(&sm.sum_total, t >> 10);  // mean, to within kNB (no overflow)
+    }
     __syncthreads();
-    {
+    const bool sorted = sm.max_total > sm.sum_total + (sm.sum_total >> 2) + 1024u;
+    if (sorted) {
         const uint32_t mx = sm.max_total;
         const int shift = mx >= 16 ? (32 - __clz(mx)) - 4 : 0;
         for (int i = threadIdx.x; i < kNB; i += kP2Threads) sm.key[i] = ((bucket_total[i] >> shift) << 10) | (uint32_t)(kNB - 1 - i);
-    }
-    __syncthreads();
-    for (int k2 = 2; k2 <= kNB; k2 <<= 1)
-        for (int j = k2 >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < kNB; i += kP2Threads) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const uint32_t a = sm.key[i], c = sm.key[ixj];
-                    if (((i & k2) == 0) ? (a < c) : (a > c)) { sm.key[i] = c; sm.key[ixj] = a; }
+        __syncthreads();
+        for (int k2 = 2; k2 <= kNB; k2 <<= 1)
+            for (int j = k2 >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < kNB; i += kP2Threads) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const uint32_t a = sm.key[i], c = sm.key[ixj];
+                        if (((i & k2) == 0) ? (a < c) : (a > c)) { sm.key[i] = c; sm.key[ixj] = a; }
+                    }
                 }
+                __syncthreads();
             }
-            __syncthreads();
-        }
+    } else {
+        for (int i = threadIdx.x; i < kNB; i += kP2Threads) sm.key[i] = (uint32_t)(kNB - 1 - i);  // bucket i at position i
+    }
     for (;;) {
         if (threadIdx.x == 0) { sm.bucket = atomicAdd(work, 1u); sm.next_seg = 0; sm.n_drain = 0; sm.overflow = 0; }
         __syncthreads();
@@ -961,6 +969,8 @@ count_buckets16_kernel(const uint32_t *__restrict__ gbuf, uint32_t cap_cb, uint3
                 const uint32_t n = part ? min(fill.y, cap_cb - cap_front) : min(fill.x, cap_front);
                 if (!n) continue;
                 const uint32_t *items = gbuf + ((uint64_t)b * n_seg + seg) * cap_cb + (part ? cap_front : 0u);
+                // (tried: reloading a register set as soon as it has been counted, and taking the tail from an over-read last chunk instead
+                // of a dependent load -- 0.57 -> 0.73 ms at 3.1 Gbp, no gain on 1/8 shards: profiles/r02_pass2_variants.txt)
                 const uint32_t n4 = n & ~3u;
                 for (uint32_t i = lane * 4u; i < n4; i += 512u) {  // four 128-bit loads in flight per lane
                     uint4 v[4];
