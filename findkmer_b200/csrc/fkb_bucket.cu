@@ -557,17 +557,24 @@ count_buckets_kernel(const uint16_t *__restrict__ gbuf, uint32_t cap_cb, uint32_
     // address order (a random order costs ~3 % in pass 2: TLB / DRAM page locality).  Every CTA sorts the 1024 keys for itself
     // (bitonic, 55 compare-exchange steps, of which 30 stay inside a warp).
     const uint32_t *bucket_total = work + 16;
-    if (threadIdx.x == 0) s_max = 0;
+    // When the largest bucket is within 25 % of the mean (uniform sequence) the order does not matter: no sort, index order.
+    __shared__ uint32_t s_sum;
+    if (threadIdx.x == 0) { s_max = 0; s_sum = 0; }
     __syncthreads();
-    for (int i = threadIdx.x; i < kNB; i += kP2Threads) atomicMax(&s_max, bucket_total[i]);
-    __syncthreads();
-    {
-        const uint32_t mx = s_max;
-        const int shift = mx >= 16 ? (32 - __clz(mx)) - 4 : 0;  // the largest bucket falls in class 8..15
-        for (int i = threadIdx.x; i < kNB; i += kP2Threads) s_key[i] = ((bucket_total[i] >> shift) << 10) | (uint32_t)(kNB - 1 - i);
+    for (int i = threadIdx.x; i < kNB; i += kP2Threads) {
+        const uint32_t t = bucket_total[i];
+        atomicMax(&s_max, t);
+        atomicAdd(&s_sum, t >> 10);  // the mean, to within kNB
     }
     __syncthreads();
-    for (int k2 = 2; k2 <= kNB; k2 <<= 1)
+    const bool sorted = s_max > s_sum + (s_sum >> 2) + 1024u;
+    {
+        const uint32_t mx = s_max;
+        const int shift = (sorted && mx >= 16) ? (32 - __clz(mx)) - 4 : 31;  // the largest bucket falls in class 8..15 (not sorted: one class)
+        for (int i = threadIdx.x; i < kNB; i += kP2Threads) s_key[i] = (((bucket_total[i] >> shift) >> (sorted ? 0 : 1)) << 10) | (uint32_t)(kNB - 1 - i);
+    }
+    __syncthreads();
+    for (int k2 = 2; sorted && k2 <= kNB; k2 <<= 1)
         for (int j = k2 >> 1; j > 0; j >>= 1) {
             for (int i = threadIdx.x; i < kNB; i += kP2Threads) {
                 const int ixj = i ^ j;
