@@ -62,6 +62,13 @@ constexpr int kDrainCap = 2048;        // drained (array, counter) pairs a bucke
 
 __device__ __forceinline__ uint32_t bucket_of(uint32_t x) { return (x << 10) >> 22; }  // bases 5..9 = bits 21..12
 
+// layout of the routed items in HBM: one segment of cap_cb items per (bucket, pass-1 CTA), [bucket][cta][cap] -- a bucket's segments are
+// neighbours (pass 2 reads one region) and a CTA's 1024 flush targets lie 12 MB apart.  The transposed layout [cta][bucket][cap] (a
+// CTA's targets within 120 MB) was measured: no difference in either pass (1.40 / 0.57 ms both ways), so TLB reach is not what
+// bounds the flush.
+__device__ __forceinline__ uint64_t seg_base(uint32_t bucket, uint32_t cta, uint32_t n_cta, uint32_t cap_cb) { return ((uint64_t)bucket * n_cta + cta) * cap_cb; }
+__device__ __forceinline__ uint64_t bucket_stride(uint32_t n_cta, uint32_t cap_cb) { return (uint64_t)n_cta * cap_cb; }
+
 // the six 11-mers of one item: every exact escape goes through here
 __device__ __noinline__ void red_kmers_of_item(uint32_t x, uint32_t *table_k, uint32_t amount)
 {
@@ -160,7 +167,7 @@ bucketize16_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers
     const uint64_t my_first = gw * q + (gw < rem ? gw : rem);
     const uint32_t max_iters = (uint32_t)(q + (rem ? 1 : 0));  // CTA-uniform trip count (barriers)
     const uint64_t region = lo + my_first * kWSpan, hi = lo + n_witers * kWSpan;
-    uint32_t *const my_gbuf = gbuf + (uint64_t)blockIdx.x * cap_cb;  // + bucket * gridDim.x * cap_cb
+    uint32_t *const my_gbuf = gbuf + seg_base(0, blockIdx.x, gridDim.x, cap_cb);  // + bucket * bucket_stride
     const bool edge_first = (lane == 0) && (region == lo), edge_last = (lane == 31) && (region + (uint64_t)my_iters * kWSpan == hi);
 
     uint32_t t_unknown = 0, t_dummy = 0, n_fast = 0;
@@ -294,7 +301,7 @@ bucketize16_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers
                     for (int n = 0; n < kItems; ++n) {
                         if (pos[n] != 0xFFFFFFFFu && pos[n] >= (uint32_t)kCap) {
                             const uint32_t qb = atomicAdd(&sm.gback[bk[n]], 1u);
-                            if (qb < cap_cb - cap_front) my_gbuf[(uint64_t)bk[n] * gridDim.x * cap_cb + cap_front + qb] = f[n];
+                            if (qb < cap_cb - cap_front) my_gbuf[(uint64_t)bk[n] * bucket_stride(gridDim.x, cap_cb) + cap_front + qb] = f[n];
                             else ovf |= 1u << n;
                         }
                     }
@@ -330,7 +337,7 @@ bucketize16_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers
             const uint32_t sub = lane >> 3, c = lane & 7;
             uint32_t n_seg;
             asm volatile("mov.u32 %0, %%nctaid.x;" : "=r"(n_seg));
-            const uint64_t bstride = (uint64_t)n_seg * cap_cb;
+            const uint64_t bstride = bucket_stride(n_seg, cap_cb);
             const uint32_t cap4 = cap_front & ~3u;
             for (uint32_t b0 = warp * 32; b0 < (uint32_t)kNB; b0 += kP1Warps * 32) {
                 const uint32_t bl = b0 + lane;
@@ -382,7 +389,7 @@ bucketize16_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers
     for (int b = threadIdx.x; b < kNB; b += kP1Threads) {
         const uint32_t cnt = min(sm.cursor[b], (uint32_t)kCap);
         uint32_t off = sm.goff[b];
-        uint32_t *dst = my_gbuf + (uint64_t)b * gridDim.x * cap_cb;
+        uint32_t *dst = my_gbuf + (uint64_t)b * bucket_stride(gridDim.x, cap_cb);
         for (uint32_t i = 0; i < cnt; ++i) {
             const uint32_t item = sm.stage[b * kCap + i];
             if (off < cap_front) dst[off++] = item;
@@ -585,12 +592,12 @@ bucketize16_ring_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_w
     if (threadIdx.x < 16) sm.ev[threadIdx.x] = 0;
     __syncthreads();
 
-    uint32_t *const my_gbuf = gbuf + (uint64_t)blockIdx.x * cap_cb;  // + bucket * gridDim.x * cap_cb
+    uint32_t *const my_gbuf = gbuf + seg_base(0, blockIdx.x, gridDim.x, cap_cb);  // + bucket * bucket_stride
     uint32_t t_unknown = 0, t_dummy = 0, n_fast = 0;
     unsigned long long t_windows = 0, t_valid = 0;
 
     {
-        const uint64_t bstride = (uint64_t)gridDim.x * cap_cb;
+        const uint64_t bstride = bucket_stride(gridDim.x, cap_cb);
         const uint64_t n_warps = (uint64_t)gridDim.x * kProdWarps, gw = (uint64_t)blockIdx.x * kProdWarps + warp;
         const uint64_t q = n_witers / n_warps, rem = n_witers % n_warps;
         const uint32_t my_iters = (uint32_t)(q + (gw < rem ? 1 : 0));
@@ -734,7 +741,7 @@ bucketize16_ring_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_w
                                 while ((((lds_volatile(ca) * 0xFFFF0001u) >> 16) & 0xFFFFu) - 0x1000u < 0x7000u) __nanosleep(200);
                             }
                             const uint32_t qb = atomicAdd(&sm.gback[bk[n]], 1u);
-                            if (qb < cap_cb - cap_front) my_gbuf[(uint64_t)bk[n] * gridDim.x * cap_cb + cap_front + qb] = f[n];
+                            if (qb < cap_cb - cap_front) my_gbuf[(uint64_t)bk[n] * bucket_stride(gridDim.x, cap_cb) + cap_front + qb] = f[n];
                             else ovf |= 1u << n;
                         }
                     }
@@ -779,7 +786,7 @@ bucketize16_ring_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_w
     for (int b = threadIdx.x; b < kNB; b += kRingThreads) {
         const uint32_t w = sm.cursor[b], lim = w & 0xFFFFu, fl = lim - (uint32_t)kCap, cnt = min(w >> 16, lim) - fl;
         uint32_t off = sm.goff[b];
-        uint32_t *dst = my_gbuf + (uint64_t)b * gridDim.x * cap_cb;
+        uint32_t *dst = my_gbuf + (uint64_t)b * bucket_stride(gridDim.x, cap_cb);
         for (uint32_t i = 0; i < cnt; ++i) {
             const uint32_t item = sm.stage[b * kCap + mod_cap(fl + i)];
             if (off < cap_front) dst[off++] = item;
@@ -968,7 +975,7 @@ count_buckets16_kernel(const uint32_t *__restrict__ gbuf, uint32_t cap_cb, uint3
             for (int part = 0; part < 2; ++part) {
                 const uint32_t n = part ? min(fill.y, cap_cb - cap_front) : min(fill.x, cap_front);
                 if (!n) continue;
-                const uint32_t *items = gbuf + ((uint64_t)b * n_seg + seg) * cap_cb + (part ? cap_front : 0u);
+                const uint32_t *items = gbuf + seg_base(b, seg, (uint32_t)n_seg, cap_cb) + (part ? cap_front : 0u);
                 // (tried: reloading a register set as soon as it has been counted, and taking the tail from an over-read last chunk instead
                 // of a dependent load -- 0.57 -> 0.73 ms at 3.1 Gbp, no gain on 1/8 shards: profiles/r02_pass2_variants.txt)
                 const uint32_t n4 = n & ~3u;
@@ -992,7 +999,7 @@ count_buckets16_kernel(const uint32_t *__restrict__ gbuf, uint32_t cap_cb, uint3
                 const uint2 fill = reinterpret_cast<const uint2 *>(gcount)[(uint64_t)b * n_seg + seg];
                 for (int part = 0; part < 2; ++part) {
                     const uint32_t n = part ? min(fill.y, cap_cb - cap_front) : min(fill.x, cap_front);
-                    const uint32_t *items = gbuf + ((uint64_t)b * n_seg + seg) * cap_cb + (part ? cap_front : 0u);
+                    const uint32_t *items = gbuf + seg_base(b, seg, (uint32_t)n_seg, cap_cb) + (part ? cap_front : 0u);
                     for (uint32_t i = lane; i < n; i += 32) red_kmers_of_item(items[i], table_k, 1u);
                 }
             }
