@@ -28,11 +28,17 @@ def reduce_accumulators(table, flags, partials, dst: int = 0, group=None, fused=
     """The one exchange step.  Tensors may live on CUDA (NCCL) or on the CPU (gloo, tests).
     `fused`: an int32 tensor that holds table and flags back to back (DeviceAccumulators.buf) -- one collective
     instead of two; flag bytes are 0/1 per rank, so their byte-wise sum is exact and "present" == non-zero."""
+    import os
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
     if fused is not None:
-        dist.reduce(fused, dst, op=dist.ReduceOp.SUM, group=group)
+        # FKB_EXCHANGE=allreduce: the same sum delivered to every rank (lets NCCL pick its NVSwitch in-network reduction); measured
+        # against the default rooted reduce in profiles/ (the counts are identical either way, only rank `dst` finalizes)
+        if os.environ.get("FKB_EXCHANGE", "reduce") == "allreduce":
+            dist.all_reduce(fused, op=dist.ReduceOp.SUM, group=group)
+        else:
+            dist.reduce(fused, dst, op=dist.ReduceOp.SUM, group=group)
     else:
         dist.reduce(table, dst, op=dist.ReduceOp.SUM, group=group)  # uint32 bit patterns in int32: wrap-around sums are exact
         dist.reduce(flags, dst, op=dist.ReduceOp.MAX, group=group)  # presence bytes: OR == max
