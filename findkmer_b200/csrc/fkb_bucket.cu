@@ -33,6 +33,10 @@
 #include "fkb_kernels.cuh"
 #include "fkb_stream.cuh"
 
+#ifndef FKB_P1_PREFETCH
+#define FKB_P1_PREFETCH 2   // L2 prefetch distance of pass 1 in iterations beyond the register pipeline (profiles/r02_prefetch.txt)
+#endif
+
 namespace fkb {
 
 namespace {
@@ -302,6 +306,13 @@ bucketize_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers, 
             Group enc[S];
             const bool ld_full = it + 3 < my_iters, ld_halo = (it + 3 == my_iters) && lane == 0;
             const uint8_t *const p3 = lane_base + (uint64_t)(it + 3) * WSPAN;
+#if FKB_P1_PREFETCH > 0
+            // the lines of iteration it + 3 + D go to L2 now (no register, no scoreboard): see fkb_bucket2.cu FKB2_PREFETCH
+            // (measured per stride, 3.1 Gbp: k = 13 / 12 (S = 1, 2) 5.91 -> 5.38 / 3.09 -> 3.00 ms; k = 10 / 9 (S = 4, 5) 1.89 -> 1.95 / 1.68 -> 1.66 ms:
+            // the long iterations of S >= 4 already cover the latency, so the prefetch is on for the short ones only)
+            if (S <= 2 && lane < (int)((WSPAN + 127) / 128) && it + 3u + FKB_P1_PREFETCH < my_iters)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(s + region + (uint64_t)(it + 3u + FKB_P1_PREFETCH) * WSPAN + (uint64_t)lane * 128u));
+#endif
             auto stage_items = [&](auto all_t) {
                 constexpr bool ALL = decltype(all_t)::value;  // every slot is emitted: no predicates at all
                 constexpr int o0 = (kW - 1) % S;

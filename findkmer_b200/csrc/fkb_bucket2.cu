@@ -51,6 +51,12 @@ constexpr int kCap = 52;               // staged items per bucket: 13 chunks of 
 #ifndef FKB2_TILE_ITERS
 #define FKB2_TILE_ITERS 6              // warp iterations between flushes: 6 * 8 * 640 / 1024 = 30 items per row on average (+ <= 3 carried) of 52
 #endif
+// L2 prefetch distance of pass 1 in iterations beyond the register pipeline.  Measured (profiles/r02_prefetch.txt, 3.1 Gbp): off 1.42 ms,
+// 1 / 2 / 3 / 4 / 8 iterations 1.32 / 1.32 / 1.33 / 1.40 / 1.62 ms.  The load-to-use distance of the register pipeline is one iteration
+// (~1.5 us), about the HBM latency under load: 26 % of the kernel's stall samples sat on the first use of the loaded bytes.
+#ifndef FKB2_PREFETCH
+#define FKB2_PREFETCH 2
+#endif
 #ifndef FKB2_P2_THREADS
 #define FKB2_P2_THREADS 1024
 #endif
@@ -258,6 +264,12 @@ bucketize16_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers
             Group enc[kG];
             const bool ld_full = it + 3 < my_iters, ld_halo = (it + 3 == my_iters) && lane == 0;
             const uint8_t *const p3 = lane_base + (uint64_t)(it + 3) * kWSpan;
+#if FKB2_PREFETCH > 0
+            // the 12 lines of iteration it + 3 + D go to L2 now (no register, no scoreboard): the load issued in iteration it + D then
+            // has one iteration (~1.5 us) to come back from L2 instead of from HBM
+            if (lane < (int)(kWSpan / 128) && it + 3u + FKB2_PREFETCH < my_iters)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(s + region + (uint64_t)(it + 3u + FKB2_PREFETCH) * kWSpan + (uint64_t)lane * 128u));
+#endif
             auto stage_items = [&](auto all_t) {
                 constexpr bool ALL = decltype(all_t)::value;
                 uint32_t f[kItems], bk[kItems], pos[kItems];
@@ -981,6 +993,7 @@ count_buckets16_kernel(const uint32_t *__restrict__ gbuf, uint32_t cap_cb, uint3
                 const uint32_t n4 = n & ~3u;
                 for (uint32_t i = lane * 4u; i < n4; i += 512u) {  // four 128-bit loads in flight per lane
                     uint4 v[4];
+                    // (an L2 prefetch of the warp's next 2 KiB steps was measured here too: 0.570 -> 0.577..0.591 ms, not kept)
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
                         v[u] = (i + 128u * u < n4) ? *reinterpret_cast<const uint4 *>(items + i + 128u * u) : make_uint4(0, 0, 0, 0);
