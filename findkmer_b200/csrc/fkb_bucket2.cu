@@ -43,13 +43,15 @@ constexpr int kItems = kCH / kStep;    // 8
 constexpr uint64_t kWSpan = 32ull * kCH;
 constexpr int kNB = 1024;              // buckets
 constexpr int kCap = 52;               // staged items per bucket: 13 chunks of 4 items = 208 bytes per row, as in fkb_bucket.cu
-// pass-1 CTA size and tile length, measured on B200 (profiles/r02_b16_variants.txt, config 4): 512 threads x 7 iterations 1.44 ms,
-// 576 x 6 1.42, 640 x 6 1.39 (102 registers: the last size without spills), 768 x 5 1.55, 1024 x 3 2.27 (64 registers: spills)
+// pass-1 CTA size and tile length, measured on B200 (config 4).  Without the L2 prefetch below the kernel was latency-bound and wanted
+// warps (profiles/r02_b16_variants.txt: 512 threads x 7 iterations 1.44 ms, 576 x 6 1.42, 640 x 6 1.39 -- the last size without
+// spills --, 768 x 5 1.55, 1024 x 3 2.27).  With it the ALU pipe and the flush bound it and fewer, fatter warps are as good or better
+// (profiles/r02_prefetch.txt: 384 x 9 1.33, 448 x 8 1.32, 512 x 6 / 7 / 8 1.32 / 1.30 / 1.30, 576 x 7 1.31, 640 x 6 1.32, 768 x 5 1.50)
 #ifndef FKB2_P1_THREADS
-#define FKB2_P1_THREADS 640
+#define FKB2_P1_THREADS 512
 #endif
 #ifndef FKB2_TILE_ITERS
-#define FKB2_TILE_ITERS 6              // warp iterations between flushes: 6 * 8 * 640 / 1024 = 30 items per row on average (+ <= 3 carried) of 52
+#define FKB2_TILE_ITERS 7              // warp iterations between flushes: 7 * 8 * 512 / 1024 = 28 items per row on average (+ <= 3 carried) of 52
 #endif
 // L2 prefetch distance of pass 1 in iterations beyond the register pipeline.  Measured (profiles/r02_prefetch.txt, 3.1 Gbp): off 1.42 ms,
 // 1 / 2 / 3 / 4 / 8 iterations 1.32 / 1.32 / 1.33 / 1.40 / 1.62 ms.  The load-to-use distance of the register pipeline is one iteration
@@ -702,6 +704,10 @@ bucketize16_ring_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_w
             Group enc[kG];
             const bool ld_full = it + 3 < my_iters, ld_halo = (it + 3 == my_iters) && lane == 0;
             const uint8_t *const p3 = lane_base + (uint64_t)(it + 3) * kWSpan;
+#if FKB2_PREFETCH > 0
+            if (lane < (int)(kWSpan / 128) && it + 3u + FKB2_PREFETCH < my_iters)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(s + region + (uint64_t)(it + 3u + FKB2_PREFETCH) * kWSpan + (uint64_t)lane * 128u));
+#endif
             auto stage_items = [&](auto all_t) {
                 constexpr bool ALL = decltype(all_t)::value;
                 uint32_t f[kItems], bk[kItems], pos[kItems];
