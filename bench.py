@@ -353,10 +353,12 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "dominant": dominant,
                 "kernel": "count path of one step: " + (shares or "bucketize_kernel + count_buckets_kernel + edges (shares: profiles/)"),
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": shard_bytes, "peak_source": peak_src, "traffic_note": traffic_note,
-                "binding_resource": "pass 1 (70 % of the count path): latency of its load + encode skeleton at 20 warps per SM (1.0 ms of 1.39 by "
-                                    "ablation) plus the synchronous flush of the staging rows (0.4 ms); its slot atomics and payload stores hide "
-                                    "behind the skeleton.  pass 2: shared-memory data pipe 75 % busy (3.3 wavefronts per counter atomic).  DRAM "
-                                    "~45 % of the copy bandwidth: not HBM bound (profiles/r02_ceiling_model.md)"}
+                "binding_resource": "pass 1 (69 % of the count path): the ALU pipe (57 % busy on average, math_pipe_throttle the second stall "
+                                    "reason; its ALU-pipe instructions alone are 0.75 ms) plus the synchronous flush of the staging rows (0.28 ms of "
+                                    "store-path time); the load latency that bound it before is hidden by an L2 prefetch two iterations beyond the "
+                                    "register pipeline (profiles/r02_prefetch.txt).  pass 2: shared-memory atomics (data pipe 76 % busy, 3.3 wavefronts "
+                                    "per counter atomic; without any load latency it would take 0.525 instead of 0.569 ms).  DRAM ~47 % of the copy "
+                                    "bandwidth: not HBM bound (profiles/r02_ceiling_model.md)"}
 
     # ---- e2e leg: raw FASTA bytes in pinned host memory -> counts on the host ----
     e2e = None
@@ -415,6 +417,26 @@ def main():
                "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps,
                "path": "raw FASTA bytes in pinned host memory -> H2D in 128 MiB chunks -> device strip (record/line compaction) -> "
                        "count -> [reduce] -> finalize -> table + counts D2H; pageable inputs use the host loader threads instead"}
+        # the same call on PAGEABLE host memory -- what the drop-in CLI does with its mmap'ed file: the host loader threads strip into
+        # pinned slots (cudaHostRegister of a file mapping is refused: profiles/r02_hostreg_probe.txt), H2D of the stripped stream
+        if world == 1:
+            import numpy as np
+            h_page = np.empty(h_raw.numel(), dtype=np.uint8)
+            h_page[:] = h_raw.numpy()
+
+            def pageable_step():
+                counter._check(lib.fkb_count_fasta_host(ctx, h_page.ctypes.data, h_page.size, k, h_table.data_ptr(), ctypes.byref(h_counts)))
+
+            pageable_step()  # warm-up: pins the loader's ring
+            t0 = time.perf_counter()
+            for _ in range(2):
+                pageable_step()
+            pg_s = (time.perf_counter() - t0) / 2
+            assert h_counts.n_kmers == expect and int(h_table.to(torch.int64).sum()) == expect
+            e2e["pageable"] = {"value": args.bases / pg_s / 1e9, "unit": UNIT, "ms_per_step": pg_s * 1e3, "steps": 2,
+                               "path": "raw FASTA bytes in pageable host memory -> host loader threads (AVX-512 strip into a ring of pinned 4 MiB "
+                                       "slots) -> H2D of the stripped stream -> count -> finalize -> table + counts D2H"}
+            del h_page
 
     # ---- secondary workload (rank 0, N = 1): BASELINE.json config 5 -- 3.1 Gbp with N runs and soft-masked lower case, k = 8 ----
     secondary = None
