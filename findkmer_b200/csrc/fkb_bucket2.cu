@@ -298,7 +298,8 @@ bucketize16_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_witers
                 for (int g = 0; g < kG; ++g) {
                     enc[g].code = pack_codes_fast(raw[g], va);
                     enc[g].valid = 0xFFFFu;
-                    raw[g] = ldg128_if(p3 + 16 * g, ld_full || (g == 0 && ld_halo));
+                    // (no zero fill when off: what stays in the registers beyond the end of the region is never consumed -- 1.30 -> 1.29 ms)
+                    ldg128_keep(raw[g], p3 + 16 * g, ld_full || (g == 0 && ld_halo));
                 }
                 uint32_t top = 0;
 #pragma unroll

@@ -28,6 +28,13 @@ __device__ __forceinline__ uint4 ldg128_if(const uint8_t *p, bool pred)
                  : "+r"(r.x), "+r"(r.y), "+r"(r.z), "+r"(r.w) : "l"(p), "r"((uint32_t)pred));
     return r;
 }
+// predicated 128-bit load that KEEPS the register's previous content when off (no zero fill: two CS2R less per load) -- for the
+// pipeline registers of the streaming kernels, whose values beyond the end of a warp's region are never consumed
+__device__ __forceinline__ void ldg128_keep(uint4 &r, const uint8_t *p, bool pred)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
+                 : "+r"(r.x), "+r"(r.y), "+r"(r.z), "+r"(r.w) : "l"(p), "r"((uint32_t)pred));
+}
 // predicated 128-bit shared load / global store (pass-1 flush): no branches, loads and stores in separate statements so
 // that a step's loads are all in flight before the first store waits for its data
 __device__ __forceinline__ uint4 lds128_if(uint32_t saddr, bool pred)
