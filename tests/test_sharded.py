@@ -52,6 +52,33 @@ def test_two_rank_gloo_shards_reduce_to_the_whole(harness, tmp_path, k):
     assert np.array_equal(np.load(out), harness.oracle_count_stream(stream, k).table)
 
 
+def _worker_fused(rank, world, port, mode, out_path):
+    import torch
+    import torch.distributed as dist
+    from findkmer_b200 import sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["FKB_EXCHANGE"] = mode
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fused = (torch.arange(4096 + 16, dtype=torch.int32) * (rank + 1)) % 1000  # table (4096) and flags (16 words) back to back, as DeviceAccumulators.buf
+    partials = torch.full((12,), rank + 1, dtype=torch.int64)
+    sharded.reduce_accumulators(fused[:4096], fused[4096:], partials, dst=0, fused=fused)
+    if rank == 0:
+        np.save(out_path, fused.numpy())
+        assert partials.tolist() == [sum(range(1, world + 1))] * 12
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["reduce", "allreduce"])
+def test_fused_exchange_modes(tmp_path, mode):
+    """the one-collective form of the exchange (table + flags in one int32 buffer), rooted reduce and FKB_EXCHANGE=allreduce"""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "fused.npy")
+    mp.spawn(_worker_fused, args=(2, _free_port(), mode, out), nprocs=2, join=True)
+    i = np.arange(4096 + 16, dtype=np.int64)
+    assert np.array_equal(np.load(out), ((i % 1000) + (2 * i) % 1000).astype(np.int32))
+
+
 def test_shard_cuts_cover_and_align():
     from findkmer_b200 import sharded
     for total in (0, 1, 15, 16, 17, 1000, 3_100_000_024):
