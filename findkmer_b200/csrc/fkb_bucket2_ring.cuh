@@ -32,9 +32,13 @@
 #ifndef FKB2_FLUSH_EVERY
 #define FKB2_FLUSH_EVERY 6             // a warp's iterations between two flushes of its rows: ~5 items per row and iteration, 52 slots
 #endif
-constexpr int kProdWarps = FKB2_PROD_WARPS, kFlushEvery = FKB2_FLUSH_EVERY;
-constexpr int kRingThreads = 32 * kProdWarps;
-constexpr int kOwn = ((kNB + kProdWarps - 1) / kProdWarps + 3) & ~3;  // rows a warp owns (52); the last warp owns what is left
+#ifndef FKB2_FLUSH_WARPS
+#define FKB2_FLUSH_WARPS 0             // > 0: that many DEDICATED flusher warps beside the producers, which then never flush (an experiment)
+#endif
+constexpr int kProdWarps = FKB2_PROD_WARPS, kFlushEvery = FKB2_FLUSH_EVERY, kFlushWarps = FKB2_FLUSH_WARPS;
+constexpr int kRingThreads = 32 * (kProdWarps + kFlushWarps);
+constexpr int kOwn = kFlushWarps ? 52 : (((kNB + kProdWarps - 1) / kProdWarps + 3) & ~3);  // rows per flush duty (52); the last group is what is left
+constexpr int kOwners = (kNB + kOwn - 1) / kOwn;
 constexpr uint32_t kRebase = kCap;  // `flushed` stays below 52, good claims below 104: slot = claimed - (claimed >= 52 ? 52 : 0)
 constexpr uint32_t kDone = 0xFFFFFFFEu;  // even: nothing in flight
 constexpr uint32_t kNotEmitted = 0x7FFF0000u;  // a "claim" that is neither good nor bad: claimed - limit = 0x7FFF
@@ -187,7 +191,15 @@ bucketize16_ring_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_w
     uint32_t t_unknown = 0, t_dummy = 0, n_fast = 0;
     unsigned long long t_windows = 0, t_valid = 0;
 
-    {
+    if (warp >= kProdWarps) {  // dedicated flusher warps (FKB2_FLUSH_WARPS > 0): walk the row groups until every producer has finished
+        const uint64_t bstride = bucket_stride(gridDim.x, cap_cb);
+        for (;;) {
+            bool done = true;
+            for (int o = warp - kProdWarps; o < kOwners; o += (kFlushWarps ? kFlushWarps : 1))
+                done = ring_flush(sm, o, lane, gbuf, my_gbuf, bstride, cap_front, table_k) && done;
+            if (done) break;
+        }
+    } else {
         const uint64_t bstride = bucket_stride(gridDim.x, cap_cb);
         const uint64_t n_warps = (uint64_t)gridDim.x * kProdWarps, gw = (uint64_t)blockIdx.x * kProdWarps + warp;
         const uint64_t q = n_witers / n_warps, rem = n_witers % n_warps;
@@ -358,7 +370,7 @@ bucketize16_ring_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_w
             for (int g = 0; g < kG; ++g) { cur[g] = nxt[g]; nxt[g] = enc[g]; }
 
             // ---- flush duty for the rows this warp owns ----
-            if (--fc == 0u) {
+            if (kFlushWarps == 0 && --fc == 0u) {
                 ring_flush(sm, warp, lane, gbuf, my_gbuf, bstride, cap_front, table_k);
                 fc = (uint32_t)kFlushEvery;
             }
@@ -366,7 +378,8 @@ bucketize16_ring_kernel(const uint8_t *__restrict__ s, uint64_t lo, uint64_t n_w
         __syncwarp();
         if (lane == 0) sts_publish(progress_sa, kDone);
         // keep serving my rows until every warp has finished; the last round starts after that and takes all whole chunks
-        while (!ring_flush(sm, warp, lane, gbuf, my_gbuf, bstride, cap_front, table_k)) __nanosleep(3000);
+        if (kFlushWarps == 0)
+            while (!ring_flush(sm, warp, lane, gbuf, my_gbuf, bstride, cap_front, table_k)) __nanosleep(3000);
     }
     __syncthreads();
 
