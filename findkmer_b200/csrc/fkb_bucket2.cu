@@ -439,7 +439,7 @@ struct P2Smem {
     uint32_t drain[kDrainCap];  // (array << 16) | index of every drained counter (128 counts each)
     uint2 fill[512];
     uint32_t key[kNB];
-    uint32_t bucket, next_seg, max_total, sum_total, n_drain, overflow;
+    uint32_t bucket, bucket_next, next_seg, max_total, sum_total, n_drain, overflow;
 };
 
 // fold one array: out index o (12 bits) at offset t (0..2) of the array's 13-mer; R = number of low bits of o that lie below the core
@@ -529,11 +529,14 @@ count_buckets16_kernel(const uint32_t *__restrict__ gbuf, uint32_t cap_cb, uint3
     } else {
         for (int i = threadIdx.x; i < kNB; i += kP2Threads) sm.key[i] = (uint32_t)(kNB - 1 - i);  // bucket i at position i
     }
+    // the next bucket's index is fetched by thread 0 while everybody folds the current one (a global atomic round trip and one CTA
+    // barrier per bucket less: the per-bucket fixed costs are what a short shard pays for, profiles/r02_pass2_variants.txt)
+    if (threadIdx.x == 0) { sm.bucket = atomicAdd(work, 1u); sm.next_seg = 0; sm.n_drain = 0; sm.overflow = 0; }
+    __syncthreads();
     for (;;) {
-        if (threadIdx.x == 0) { sm.bucket = atomicAdd(work, 1u); sm.next_seg = 0; sm.n_drain = 0; sm.overflow = 0; }
-        __syncthreads();
-        if (sm.bucket >= (uint32_t)kNB) break;
-        const uint32_t b = (uint32_t)(kNB - 1) - (sm.key[sm.bucket] & (uint32_t)(kNB - 1));
+        const uint32_t cur_bucket = sm.bucket;
+        if (cur_bucket >= (uint32_t)kNB) break;
+        const uint32_t b = (uint32_t)(kNB - 1) - (sm.key[cur_bucket] & (uint32_t)(kNB - 1));
         for (int i = threadIdx.x; i < 32768 / 4; i += kP2Threads) reinterpret_cast<uint4 *>(sm.cnt)[i] = make_uint4(0, 0, 0, 0);
         for (int i = threadIdx.x; i < n_seg && i < 512; i += kP2Threads) sm.fill[i] = reinterpret_cast<const uint2 *>(gcount)[(uint64_t)b * n_seg + i];
         __syncthreads();
@@ -611,7 +614,9 @@ count_buckets16_kernel(const uint32_t *__restrict__ gbuf, uint32_t cap_cb, uint3
             }
         }
         __syncthreads();
-        if (sm.overflow) {
+        const uint32_t was_overflow = sm.overflow, n_drained = sm.n_drain;
+        if (threadIdx.x == 0) sm.bucket_next = atomicAdd(work, 1u);
+        if (was_overflow) {
             // A byte wrapped (or the drain list ran over): the counters are meaningless.  Nothing of this bucket has reached T_k yet:
             // recount it exactly, six global reds per item.
             for (uint32_t seg = threadIdx.x >> 5; seg < (uint32_t)n_seg; seg += kP2Threads / 32) {
@@ -630,9 +635,10 @@ count_buckets16_kernel(const uint32_t *__restrict__ gbuf, uint32_t cap_cb, uint3
             fold_array<0, 8>(cb, b, table_k);
             fold_array<1, 10>(cb, b, table_k);
             fold_array<2, 12>(cb, b, table_k);
-            const uint32_t nd = min(sm.n_drain, (uint32_t)kDrainCap);
+            const uint32_t nd = min(n_drained, (uint32_t)kDrainCap);
             for (uint32_t i = threadIdx.x; i < nd; i += kP2Threads) red_kmers_of_counter(sm.drain[i] >> 16, sm.drain[i] & 0xFFFFu, b, table_k, 128u);
         }
+        if (threadIdx.x == 0) { sm.bucket = sm.bucket_next; sm.next_seg = 0; sm.n_drain = 0; sm.overflow = 0; }
         __syncthreads();
     }
 }
